@@ -1,0 +1,235 @@
+/*
+ * rpcc_b200.h -- C ABI of librpcc_b200.so: the B200 (sm_100a) implementation of R-PCC's
+ * per-frame compression hot path (project -> FPS segment -> model -> quantize -> pack,
+ * plus decode and chamfer evaluation).
+ *
+ * This is the drop-in boundary.  The reference crosses it through pybind11 modules
+ * (ops/cpp_modules/src/cpp_modules.cpp:597-636), a torch CUDAExtension
+ * (ops/fps/src/fps_api.cpp:7-9) and a JIT torch extension
+ * (utils/ChamferDistancePytorch/chamfer3D/chamfer_cuda.cpp:17-30).  Every entry point below
+ * names the reference interface it replaces.  Signatures use plain pointers and sizes only
+ * (no torch / numpy / pybind types); INTEGRATION.md shows the ctypes binding the reference
+ * side would add.
+ *
+ * Conventions
+ *  - All functions return 0 (RPCC_OK) or a negative RPCC_ERR_* code; rpcc_last_error()
+ *    returns a thread-local message.  Nothing calls exit() (the reference's FPS glue does,
+ *    ops/fps/src/sampling.cpp:9-21).
+ *  - `*_batch` functions take DEVICE pointers, enqueue on `stream` (a cudaStream_t passed as
+ *    void*; NULL = legacy default stream) and do not synchronise.  Buffers are caller-owned.
+ *  - `rpcc_op_*` functions take HOST pointers, one frame, and are synchronous: they are the
+ *    one-to-one replacements of the reference's pybind functions (numpy in, numpy out).
+ *  - Frames of a batch are laid out frame-major: range images [B][H][W] f32, labels
+ *    [B][H][W] u8 (device) / int32 (host ops, as the reference), etc.
+ *  - Labels: 0 = ground, 1 = empty pixel, 2..cluster_num+1 = FPS clusters
+ *    (utils/segment_utils.py:168-169).  K = cluster_num + 2 model rows.
+ */
+#ifndef RPCC_B200_H_
+#define RPCC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define RPCC_API __attribute__((visibility("default")))
+#else
+#define RPCC_API
+#endif
+
+#define RPCC_OK 0
+#define RPCC_ERR_ARG (-1)     /* bad argument (null pointer, size out of range) */
+#define RPCC_ERR_CUDA (-2)    /* CUDA runtime error, see rpcc_last_error() */
+#define RPCC_ERR_NO_DEVICE (-3)
+#define RPCC_ERR_CAPACITY (-4) /* caller-provided buffer too small / batch larger than the encoder's */
+
+#define RPCC_MAX_LABELS 256   /* labels are stored as u8 on device; K = cluster_num + 2 <= 254 */
+#define RPCC_TILE 1024        /* pixels per rank tile (flat raster index / 1024) */
+
+RPCC_API const char* rpcc_last_error(void);
+RPCC_API int rpcc_version(void);
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+RPCC_API long long rpcc_launch_count(void);
+RPCC_API int rpcc_device_count(void);
+
+/* ---- a1. dataset/transformer.py:41-54 create_transform_map (host, f64 trig -> f32) ------------ */
+RPCC_API int rpcc_transform_map(int H, int W, double hfov, double vmax, double vmin, float* lut_host);
+
+/* ================================ device batch stages ======================================== */
+
+/* a2. cpp_modules.cpp:427-467 point_cloud_to_range_image_even, B frames per launch.
+ * points: packed rows of `stride` floats (3 = xyz, 4 = KITTI .bin x,y,z,intensity); for stride 4
+ * the base must be 16-byte aligned.  offsets[B+1]: first row of each frame (int64, device).
+ * range: [B][H][W] f32, fully overwritten (0 = empty pixel).  scratch: int32[B] (zero-depth
+ * bookkeeping).  Bit-exact with the reference for finite inputs. */
+RPCC_API int rpcc_project_batch(const float* points, int stride, const int64_t* offsets, int B, int H, int W,
+                       float hfov, float vmax, float vmin, float* range, int32_t* scratch, void* stream);
+
+/* a3. dataset/transformer.py:94-101 range_image_to_point_cloud: xyz[b][h][w][3] = range * lut. */
+RPCC_API int rpcc_range_to_xyz_batch(const float* range, const float* lut, int B, int HW, float* xyz, void* stream);
+
+/* a4 (first half). deterministic ground plane fit replacing open3d segment_plane
+ * (utils/segment_utils.py:74-82,101-108).  ground: [B][4] f32 unit-normal plane. */
+RPCC_API int rpcc_ground_fit_batch(const float* range, const float* lut, int B, int H, int W,
+                          uint64_t seed, float* ground, void* workspace, size_t workspace_bytes, void* stream);
+RPCC_API size_t rpcc_ground_fit_workspace(int B, int H, int W);
+
+/* a5. ops/fps/src/sampling_gpu.cu:24-184 furthest_point_sampling_kernel_launcher.
+ * points [B][n][3] f32 -> idx [B][m] i32.  Same seeds as the reference kernel, including its
+ * FMA pattern and tie rule.  temp: [B][n] f32 scratch (the reference's `temp`;
+ * contents on entry are ignored -- it is always (re)filled with 1e10). */
+RPCC_API int rpcc_fps_batch(const float* points, int B, int n, int m, float* temp, int32_t* idx, void* stream);
+
+/* a4+a5 fused (utils/segment_utils.py:133-141): non-ground mask + FPS straight from the range
+ * image; never materialises xyz.  center_idx [B][m] i32 (flat pixel index), centers [B][m][3]. */
+RPCC_API int rpcc_segment_fps_batch(const float* range, const float* lut, const float* ground, int B, int H, int W,
+                           int m, float ground_thr, int32_t* center_idx, float* centers, void* stream);
+
+/* Per-frame result table (device or host copy, frame-major). */
+typedef struct rpcc_frame_result {
+  uint32_t sym_count;   /* int16 symbols = non-empty pixels */
+  uint32_t seq_count;   /* uint16 idx_sequence entries */
+  uint32_t model_rows;  /* highest label present + 1: rows of plane_param the reference writes */
+  uint32_t flags;       /* bit0: exact-mean guard tripped (handled), bit1: a label >= K was seen */
+} rpcc_frame_result;
+
+/* Bookkeeping workspace shared by assign/label_stats -> point_model -> quantize_pack (device,
+ * opaque; tile histograms, label counts, exact sums, offsets).  K = number of model rows. */
+RPCC_API size_t rpcc_book_bytes(int B, int H, int W, int K);
+
+/* a4 (second half, utils/segment_utils.py:143-148,168-169) + a6 accumulation
+ * (cpp_modules.cpp:471-518): per-pixel argmin over {ground, m centres} with torch's float32
+ * arithmetic.  labels [B][HW] u8.  Fills `book` (K = m + 2) for the next two stages. */
+RPCC_API int rpcc_assign_labels_batch(const float* range, const float* lut, const float* ground, const float* centers,
+                             int B, int H, int W, int m, uint8_t* labels, void* book, void* stream);
+
+/* Same bookkeeping for callers that bring their own labels (the standalone quantize ops). */
+RPCC_API int rpcc_label_stats_batch(const float* range, const uint8_t* labels, int B, int H, int W, int K,
+                           void* book, void* stream);
+
+/* a6. point models + stable-order bookkeeping.  model [B][K][4] f32 rows exactly as they reach
+ * the bitstream (row 0 = ground, row 1 = 0, row l = [0,0,0,mean_l]; empty cluster = NaN as the
+ * reference); results [B] (sym_count, seq_count, model_rows, flags). */
+RPCC_API int rpcc_point_model_batch(const float* range, const uint8_t* labels, const float* ground, void* book,
+                           int B, int H, int W, int K, float* model, rpcc_frame_result* results, void* stream);
+
+/* a7+a8+a10. cpp_modules.cpp:248-285 intra_predict, :288-334 uniform_quantize (or :337-424 with
+ * per-label steps), :521-558 extract_contour + np.packbits, fused.  step_per_label: NULL =>
+ * uniform `step`; else [B][K] f32.  symbols: [B][sym_stride] i16 (first sym_count[b] valid),
+ * label-major / raster-within-label.  contour_bits [B][ceil(HW/8)] u8 MSB-first;
+ * seq [B][seq_stride] u16 (first seq_count[b] valid).  `book` must have been through
+ * rpcc_point_model_batch (or rpcc_book_offsets_batch). */
+RPCC_API int rpcc_quantize_pack_batch(const float* range, const uint8_t* labels, const float* model, const float* lut,
+                             void* book, const float* step_per_label, float step, int B, int H, int W, int K,
+                             int16_t* symbols, size_t sym_stride, uint8_t* contour_bits, uint16_t* seq,
+                             size_t seq_stride, void* stream);
+
+/* a9. cpp_modules.cpp:28-121 extract_features_with_segment (+:10-25) and the salience rule of
+ * :388-405.  key_points [B][HW] u8 (0..3); salience [B][K] u8; step_per_label [B][K] f32. */
+RPCC_API int rpcc_keypoints_salience_batch(const float* range, const uint8_t* labels, const uint32_t* label_cnt,
+                                  int B, int H, int W, int K, int region, int segments, int sharp_num,
+                                  int less_sharp_num, int flat_num, const int32_t* level_kp_num,
+                                  const float* level_acc, int level_num, int ground_level,
+                                  uint8_t* key_points, uint8_t* salience, float* step_per_label, void* stream);
+
+/* a11. decode: cpp_modules.cpp:561-593 recover_map, utils/compress_utils.py:114-132
+ * dequantize_residual, cpp_modules.cpp:248-285 intra_predict, dataset/transformer.py:94-101.
+ * contour_bits [B][ceil(HW/8)], seq [B][seq_stride] u16, symbols [B][sym_stride] i16,
+ * model [B][K][4]; steps [B][K] f64 (per-label dequantisation step).
+ * Outputs: labels [B][HW] u8, range_rec [B][HW] f32, xyz [B][HW][3] f32 (may be NULL). */
+RPCC_API int rpcc_decode_batch(const uint8_t* contour_bits, const uint16_t* seq, int seq_stride, const int16_t* symbols,
+                      int sym_stride, const float* model, const double* steps, const float* lut,
+                      int B, int H, int W, int K, uint8_t* labels, float* range_rec, float* xyz,
+                      void* workspace, size_t workspace_bytes, void* stream);
+RPCC_API size_t rpcc_decode_workspace(int B, int H, int W, int K);
+
+/* a12. chamfer3D.cu:12-154 NmDistanceKernel both ways: for each point of xyz1 [n][3] the squared
+ * distance to and index of its nearest neighbour in xyz2 [m][3], and vice versa.  Exact brute
+ * force, first-minimum tie rule as the reference. */
+RPCC_API int rpcc_chamfer_batch(const float* xyz1, int n, const float* xyz2, int m, float* dist1, int32_t* idx1,
+                       float* dist2, int32_t* idx2, void* stream);
+
+/* ================================ host (numpy-facing) ops ==================================== */
+/* One frame, host pointers, synchronous; argument meaning follows the reference's pybind
+ * functions so the reference's L3 Python can bind them one for one. */
+
+/* dataset_utils_cpp.point_cloud_to_range_image_even (cpp_modules.cpp:427) */
+RPCC_API int rpcc_op_point_cloud_to_range_image_even(const float* points, int64_t n, int stride, int H, int W,
+                                            float hfov, float vmax, float vmin, float* range_out);
+/* segment_utils_cpp.point_modeling (cpp_modules.cpp:471): out has max_label+1 floats; *K_out. */
+RPCC_API int rpcc_op_point_modeling(const float* range, const int32_t* seg, int H, int W, float* out, int cap, int* K_out);
+/* segment_utils_cpp.intra_predict (cpp_modules.cpp:248) */
+RPCC_API int rpcc_op_intra_predict(const int32_t* seg, const float* model, int K, const float* lut, int H, int W, float* pred);
+/* quantization_utils_cpp.uniform_quantize (cpp_modules.cpp:288): out cap >= H*W; *n_out. */
+RPCC_API int rpcc_op_uniform_quantize(const int32_t* seg, const float* residual, int H, int W, float acc,
+                             int32_t* out, int64_t* n_out);
+/* feature_extractor_cpp.extract_features_with_segment (cpp_modules.cpp:28) -> key_point_map */
+RPCC_API int rpcc_op_extract_features_with_segment(const float* range, const int32_t* seg, int H, int W, int region,
+                                          int segments, int sharp_num, int less_sharp_num, int flat_num,
+                                          int32_t* key_point_map);
+/* quantization_utils_cpp.nonuniform_quantize (cpp_modules.cpp:337) */
+RPCC_API int rpcc_op_nonuniform_quantize(const int32_t* seg, const float* residual, const int32_t* key_point_map,
+                                int H, int W, const int32_t* level_kp_num, const float* level_acc, int level_num,
+                                int ground_level, int32_t* out, int64_t* n_out, int32_t* salience, int* K_out);
+/* contour_utils_cpp.extract_contour (cpp_modules.cpp:521): contour [H][W] i32, seq cap H*W. */
+RPCC_API int rpcc_op_extract_contour(const int32_t* seg, int H, int W, int32_t* contour, int32_t* seq, int64_t* L_out);
+/* contour_utils_cpp.recover_map (cpp_modules.cpp:561) */
+RPCC_API int rpcc_op_recover_map(const int32_t* contour, const int32_t* seq, int64_t L, int H, int W, int32_t* seg_out);
+/* furthest_point_sampling_wrapper (ops/fps/src/sampling.cpp:24) with host arrays. */
+RPCC_API int rpcc_op_furthest_point_sample(const float* points, int B, int n, int m, int32_t* idx_out);
+/* PointCloudSegment.segment GPU branch given the ground model (utils/segment_utils.py:133-148,168-169).
+ * seg_out [H][W] i32, center_idx_out [m] i32 (may be NULL). */
+RPCC_API int rpcc_op_segment(const float* range, const float* lut, const float* ground, int H, int W, int m,
+                    float ground_thr, int32_t* seg_out, int32_t* center_idx_out);
+/* chamfer_3D.forward (chamfer_cuda.cpp:17) with host arrays, B = 1. */
+RPCC_API int rpcc_op_chamfer(const float* xyz1, int n, const float* xyz2, int m, float* dist1, int32_t* idx1,
+                    float* dist2, int32_t* idx2);
+
+/* ================================ batched encoder / decoder =================================== */
+typedef struct rpcc_encoder rpcc_encoder;
+
+typedef struct rpcc_encoder_config {
+  int H, W;
+  double hfov, vmax, vmin;     /* radians, as dataset/transformer.py:32-34 computes them */
+  int cluster_num;             /* cfgs/compressor.yaml:22 */
+  float ground_threshold;      /* cfgs/compressor.yaml:21 */
+  double step;                 /* 2 * accuracy (tools/compress.py:46) */
+  int nonuniform;              /* 0 uniform, 1 non-uniform */
+  int level_num;               /* non-uniform: cfgs/compressor.yaml:7-14 */
+  int level_kp_num[8];
+  double level_dacc[8];
+  int ground_level, feature_region, segments, sharp_num, less_sharp_num, flat_num;
+  int max_batch;               /* frames per call */
+  int64_t max_points;          /* total point rows per call */
+  int device;                  /* CUDA device ordinal */
+} rpcc_encoder_config;
+
+RPCC_API int rpcc_encoder_create(const rpcc_encoder_config* cfg, rpcc_encoder** out);
+RPCC_API void rpcc_encoder_destroy(rpcc_encoder* enc);
+/* Device-resident inputs (bench `value`): points/offsets as rpcc_project_batch; ground_in NULL =>
+ * fitted on device, else [B][4] f32 device.  Results stay in the encoder's device buffers
+ * (rpcc_encoder_device_buffers).  Enqueues on the encoder's stream; no sync. */
+RPCC_API int rpcc_encoder_encode_device(rpcc_encoder* enc, const float* points, int stride, const int64_t* offsets,
+                               int B, const float* ground_in);
+/* Host inputs/outputs (bench `e2e`, and what tools/compress_datalist.py would call): copies
+ * points H2D from `points_host` (pinned or pageable), runs the chain, copies the sections back:
+ *   results [B]; model [B][K][4] f32; contour_bits [B][ceil(HW/8)]; seq packed (sum seq_count) u16;
+ *   symbols packed (sum sym_count) i16; salience [B][K] u8 (non-uniform, else may be NULL).
+ * Synchronous.  ground_host NULL => fitted on device. */
+RPCC_API int rpcc_encoder_encode_host(rpcc_encoder* enc, const float* points_host, int stride, const int64_t* offsets_host,
+                             int B, const float* ground_host, rpcc_frame_result* results, float* model,
+                             uint8_t* contour_bits, uint16_t* seq, size_t seq_cap, int16_t* symbols,
+                             size_t sym_cap, uint8_t* salience);
+RPCC_API int rpcc_encoder_sync(rpcc_encoder* enc);
+RPCC_API void* rpcc_encoder_stream(rpcc_encoder* enc);
+/* Named device buffers of the last encode (for tests): "range","labels","model","symbols","seq",
+ * "contour","results","center_idx","ground","key_points","salience". Returns NULL if unknown. */
+RPCC_API void* rpcc_encoder_device_buffer(rpcc_encoder* enc, const char* name);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RPCC_B200_H_ */

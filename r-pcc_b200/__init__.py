@@ -1,0 +1,12 @@
+"""rpcc_b200 -- B200-native (sm_100a) implementation of R-PCC's per-frame compression hot path.
+
+Host code is Python over a C-ABI CUDA library (include/rpcc_b200.h, r-pcc_b200/csrc).  The
+package mirrors the reference's interface for this path: `plugin/*` are the drop-in
+replacements of the reference's pybind modules, `api.py` holds the L3 classes
+(PCTransformer, PointCloudSegment, QuantizationModule, ...), `batch.py` the batched encoder.
+There is no CPU fallback: every compute call needs librpcc_b200.so and a CUDA device.
+"""
+from ._lib import RpccError, build, launch_count, lib  # noqa: F401
+from .lidar import LIDAR_TABLE, LidarConfig  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,218 @@
+// assign.cu -- stage 2b + stage 3 accumulation.
+//
+// Replaces the torch eager block of PointCloudSegment.segment
+// (utils/segment_utils.py:143-148,168-169: ground residual along the ray, 100 centre distances,
+// argmax of -|.|, relabel) -- which materialises a (H,W,100,3) temporary of 153.6 MB per frame --
+// by one fused per-pixel kernel, and accumulates what point_modeling
+// (ops/cpp_modules/src/cpp_modules.cpp:471-518) and the stable label-major symbol order need.
+//
+// Arithmetic: every torch op is its own kernel, so each elementwise result is
+// rounded to f32 before the next; size-3 reductions associate as torch_sum3 (common.cuh).
+//   channel 0   : | range - ( -g3 / sum3(g*lut) ) |
+//   channel c>=1: sqrt( sum3( (pc - centre_c)^2 ) )          pc = range * lut
+//   label = first argmin; label>0 -> +1; range==0 -> 1
+// The sqrt is only taken when a squared distance undercuts every earlier one (sqrt is monotone,
+// so a candidate that is not a running minimum of the squares cannot be a strict minimum of the
+// roots); this keeps the first-index tie rule of torch.max bit-exact.
+//
+// Per-label statistics are exact: range * 2^28 is an integer for range in [2^-5, 256), summed in
+// u64 -- identical to the reference's double accumulation in raster order, whose partial sums are
+// then all exactly representable.  Ranges outside that interval raise flags bit 0 and
+// the frame's means are recomputed sequentially by model.cu.
+#include "book.cuh"
+
+namespace rpcc {
+
+constexpr int kTile = RPCC_TILE;  // 1024 threads, one pixel each
+
+// One warp-level pass per distinct label in the warp: count + exact range sum into shared bins.
+__device__ __forceinline__ void warp_label_stats(int label, bool active, float r, unsigned* s_cnt,
+                                                 unsigned long long* s_sum, unsigned* s_flag) {
+  const unsigned lane = threadIdx.x & 31;
+  unsigned todo = __ballot_sync(0xffffffffu, active);
+  const bool exact = !(active && label >= 2) || (r >= 0.03125f && r < 256.0f);
+  if (__any_sync(0xffffffffu, !exact) && lane == 0) atomicOr(s_flag, 1u);
+  const unsigned long long v = active ? (unsigned long long)((double)r * 268435456.0) : 0ull;
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    const int l = __shfl_sync(0xffffffffu, label, leader);
+    const bool mine = active && label == l;
+    const unsigned grp = __ballot_sync(0xffffffffu, mine);
+    // v < 2^36: split so that 32 addends cannot overflow 32 bits
+    const unsigned lo = mine ? (unsigned)(v & 0xFFFFFu) : 0u;
+    const unsigned hi = mine ? (unsigned)(v >> 20) : 0u;
+    const unsigned slo = __reduce_add_sync(0xffffffffu, lo);
+    const unsigned shi = __reduce_add_sync(0xffffffffu, hi);
+    if (lane == (unsigned)leader) {
+      atomicAdd(&s_cnt[l], (unsigned)__popc(grp));
+      if (l >= 2) atomicAdd(&s_sum[l], ((unsigned long long)shi << 20) + slo);
+    }
+    todo &= ~grp;
+  }
+}
+
+// Contour bits inside the tile (extract_contour, cpp_modules.cpp:534-545): a pixel starts a run when
+// it is in column 0 or its label differs from its left neighbour.  The tile's first pixel needs the
+// previous tile's last label, so it is left to model.cu; everything else is counted here.
+__device__ __forceinline__ void tile_contour_count(int label, bool inb, int p, int W, unsigned* s_last, unsigned* s_ccnt) {
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 31) s_last[warp] = (unsigned)label;
+  __syncthreads();
+  int left = __shfl_up_sync(0xffffffffu, label, 1);
+  if (lane == 0 && warp > 0) left = (int)s_last[warp - 1];
+  const bool c = inb && threadIdx.x > 0 && ((p % W) == 0 || label != left);
+  const unsigned b = __ballot_sync(0xffffffffu, c);
+  if (lane == 0 && b) atomicAdd(s_ccnt, (unsigned)__popc(b));
+}
+
+__device__ __forceinline__ void flush_tile_stats(int K, int f, int tile, int T, const unsigned* s_cnt,
+                                                 const unsigned long long* s_sum, const unsigned* s_flag,
+                                                 const unsigned* s_ccnt, const Book& bk) {
+  for (int l = threadIdx.x; l < K; l += blockDim.x) {
+    const unsigned c = s_cnt[l];
+    bk.tile_hist[((size_t)f * T + tile) * K + l] = (uint16_t)c;
+    if (c) {
+      atomicAdd(&bk.label_cnt[(size_t)f * K + l], c);
+      if (l >= 2) atomicAdd(&bk.label_sum[(size_t)f * K + l], s_sum[l]);
+    }
+  }
+  if (threadIdx.x == 0) {
+    bk.tile_ccnt[(size_t)f * T + tile] = (uint16_t)*s_ccnt;
+    if (*s_flag) atomicOr(&bk.flags[f], *s_flag);
+  }
+}
+
+__global__ void __launch_bounds__(kTile, 2)
+assign_labels_kernel(const float* __restrict__ range, const float* __restrict__ lut, const float* __restrict__ ground,
+                     const float* __restrict__ centers, int HW, int W, int m, int T, uint8_t* __restrict__ labels,
+                     Book bk) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int K = m + 2;
+  float4* s_c = reinterpret_cast<float4*>(smem_raw);                               // [m] centres
+  unsigned long long* s_sum = reinterpret_cast<unsigned long long*>(s_c + m);     // [K]
+  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_sum + K);                       // [K]
+  unsigned* s_flag = s_cnt + K;
+  unsigned* s_ccnt = s_flag + 1;
+  unsigned* s_last = s_ccnt + 1;                                                  // [32]
+
+  const int f = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+  for (int c = tid; c < m; c += kTile) {
+    const float* cp = centers + ((size_t)f * m + c) * 3;
+    s_c[c] = make_float4(cp[0], cp[1], cp[2], 0.f);
+  }
+  for (int l = tid; l < K; l += kTile) { s_cnt[l] = 0; s_sum[l] = 0; }
+  if (tid == 0) { *s_flag = 0; *s_ccnt = 0; }
+  __syncthreads();
+
+  const int p = tile * kTile + tid;
+  const bool inb = p < HW;
+  int label = 1;
+  float r = 0.f;
+  if (inb) {
+    r = range[(size_t)f * HW + p];
+    if (r != 0.0f) {
+      const float t0 = lut[(size_t)p * 3], t1 = lut[(size_t)p * 3 + 1], t2 = lut[(size_t)p * 3 + 2];
+      const float g0 = ground[f * 4], g1 = ground[f * 4 + 1], g2 = ground[f * 4 + 2], g3 = ground[f * 4 + 3];
+      const float x = r * t0, y = r * t1, z = r * t2;
+      const float rplane = (-g3) / torch_sum3(g0 * t0, g1 * t1, g2 * t2);
+      float best = fabsf(r - rplane);
+      int bi = 0;
+      float thresh = __int_as_float(0x7f800000);  // +inf: smallest squared distance examined so far
+#pragma unroll 4
+      for (int c = 0; c < m; ++c) {
+        const float4 cc = s_c[c];
+        const float dx = x - cc.x, dy = y - cc.y, dz = z - cc.z;
+        const float ss = torch_sum3(dx * dx, dy * dy, dz * dz);
+        if (ss < thresh) {
+          thresh = ss;
+          const float v = sqrtf(ss);
+          if (v < best) { best = v; bi = c + 1; }
+        }
+      }
+      label = bi > 0 ? bi + 1 : 0;
+    }
+    labels[(size_t)f * HW + p] = (uint8_t)label;
+  }
+  warp_label_stats(label, inb, r, s_cnt, s_sum, s_flag);
+  tile_contour_count(label, inb, p, W, s_last, s_ccnt);
+  __syncthreads();
+  flush_tile_stats(K, f, tile, T, s_cnt, s_sum, s_flag, s_ccnt, bk);
+}
+
+// statistics only (caller-supplied labels)
+__global__ void __launch_bounds__(kTile, 2)
+label_stats_kernel(const float* __restrict__ range, const uint8_t* __restrict__ labels, int HW, int W, int K, int T,
+                   Book bk) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* s_sum = reinterpret_cast<unsigned long long*>(smem_raw);
+  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_sum + K);
+  unsigned* s_flag = s_cnt + K;
+  unsigned* s_ccnt = s_flag + 1;
+  unsigned* s_last = s_ccnt + 1;
+  const int f = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+  for (int l = tid; l < K; l += kTile) { s_cnt[l] = 0; s_sum[l] = 0; }
+  if (tid == 0) { *s_flag = 0; *s_ccnt = 0; }
+  __syncthreads();
+  const int p = tile * kTile + tid;
+  const bool inb = p < HW;
+  int label = 1;
+  float r = 0.f;
+  if (inb) {
+    label = labels[(size_t)f * HW + p];
+    r = range[(size_t)f * HW + p];
+    if (label >= K) { label = K - 1; atomicOr(s_flag, 2u); }
+  }
+  warp_label_stats(label, inb, r, s_cnt, s_sum, s_flag);
+  tile_contour_count(label, inb, p, W, s_last, s_ccnt);
+  __syncthreads();
+  flush_tile_stats(K, f, tile, T, s_cnt, s_sum, s_flag, s_ccnt, bk);
+}
+
+}  // namespace rpcc
+
+using namespace rpcc;
+
+static int zero_book(const Book& bk, int B, int K, cudaStream_t st) {
+  RPCC_CUDA(cudaMemsetAsync(bk.label_sum, 0, book_zero_bytes(B, K), st));
+  RPCC_CUDA(cudaMemsetAsync(bk.flags, 0, sizeof(unsigned) * (size_t)B, st));
+  return RPCC_OK;
+}
+
+extern "C" size_t rpcc_book_bytes(int B, int H, int W, int K) {
+  const int T = (H * W + kTile - 1) / kTile;
+  return book_bytes(B, T, K);
+}
+
+extern "C" int rpcc_assign_labels_batch(const float* range, const float* lut, const float* ground, const float* centers,
+                                        int B, int H, int W, int m, uint8_t* labels, void* book, void* stream) {
+  RPCC_REQUIRE(range && lut && ground && centers && labels && book, "null pointer");
+  RPCC_REQUIRE(m >= 1 && m + 2 <= RPCC_MAX_LABELS, "cluster_num must be in [1, 254]");
+  RPCC_REQUIRE(B <= 65535, "at most 65535 frames per launch");
+  if (B == 0) return RPCC_OK;
+  const int HW = H * W, K = m + 2, T = (HW + kTile - 1) / kTile;
+  cudaStream_t st = as_stream(stream);
+  const Book bk = make_book(book, B, T, K);
+  int rc = zero_book(bk, B, K, st);
+  if (rc != RPCC_OK) return rc;
+  const size_t smem = sizeof(float4) * m + (sizeof(unsigned long long) + sizeof(unsigned)) * K + sizeof(unsigned) * 34;
+  assign_labels_kernel<<<dim3(T, B), kTile, smem, st>>>(range, lut, ground, centers, HW, W, m, T, labels, bk);
+  RPCC_LAUNCH_CHECK("assign_labels_kernel");
+  return RPCC_OK;
+}
+
+extern "C" int rpcc_label_stats_batch(const float* range, const uint8_t* labels, int B, int H, int W, int K,
+                                      void* book, void* stream) {
+  RPCC_REQUIRE(range && labels && book, "null pointer");
+  RPCC_REQUIRE(K >= 2 && K <= RPCC_MAX_LABELS, "K must be in [2, 256]");
+  RPCC_REQUIRE(B <= 65535, "at most 65535 frames per launch");
+  if (B == 0) return RPCC_OK;
+  const int HW = H * W, T = (HW + kTile - 1) / kTile;
+  cudaStream_t st = as_stream(stream);
+  const Book bk = make_book(book, B, T, K);
+  int rc = zero_book(bk, B, K, st);
+  if (rc != RPCC_OK) return rc;
+  const size_t smem = (sizeof(unsigned long long) + sizeof(unsigned)) * K + sizeof(unsigned) * 34;
+  label_stats_kernel<<<dim3(T, B), kTile, smem, st>>>(range, labels, HW, W, K, T, bk);
+  RPCC_LAUNCH_CHECK("label_stats_kernel");
+  return RPCC_OK;
+}

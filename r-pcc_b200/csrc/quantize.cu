@@ -1,0 +1,141 @@
+// quantize.cu -- stage 4: intra-prediction + residual quantisation + stable label-major scatter
+// + contour bitmap / index sequence, fused in one pass over the range image.
+//
+// Replaces, per pixel and bit for bit:
+//   segment_utils_cpp.intra_predict        (ops/cpp_modules/src/cpp_modules.cpp:248-285)
+//   residual = range - pred                (tools/compress.py:106, numpy f32)
+//   quantization_utils_cpp.uniform_quantize / nonuniform_quantize   (:288-334 / :337-424):
+//       q = (int)roundf(residual / step_l), emitted label-major (0,2,3,..), raster inside a label
+//   .astype(np.int16)                      (utils/compress_utils.py:142, wraps)
+//   contour_utils_cpp.extract_contour + np.packbits + astype(uint16)   (:521-558, compress_utils.py:155-160)
+//
+// HBM-bound: reads 4 B (range) + 1 B (label) per pixel, writes 2 B per valid pixel + 1 bit per pixel
+// + 2 B per run.  One CTA = one 1024-pixel tile (one pixel per thread).  The stable rank of a pixel
+// inside (tile, label) comes from match_any inside its warp plus a per-label scan over the 32 warps
+// in shared memory; the tile's base comes from tile_off (model.cu).
+#include "book.cuh"
+
+namespace rpcc {
+
+constexpr int kQThreads = RPCC_TILE;
+
+__device__ __forceinline__ float predict_range(const float4 m, const float* __restrict__ lut3) {
+  // cpp_modules.cpp:271-279
+  if (m.x + m.y + m.z == 0) return m.w;
+  return -m.w / (m.x * lut3[0] + m.y * lut3[1] + m.z * lut3[2]);
+}
+
+__global__ void __launch_bounds__(kQThreads, 1)
+quantize_pack_kernel(const float* __restrict__ range, const uint8_t* __restrict__ labels, const float* __restrict__ model,
+                     const float* __restrict__ lut, Book bk, const float* __restrict__ step_per_label, float step,
+                     int HW, int W, int K, int T, int16_t* __restrict__ symbols, size_t sym_stride,
+                     uint8_t* __restrict__ contour_bits, int cbytes, uint16_t* __restrict__ seq, size_t seq_stride) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* s_model = reinterpret_cast<float4*>(smem_raw);            // [K]
+  float* s_step = reinterpret_cast<float*>(s_model + K);            // [K]
+  unsigned* s_tb = reinterpret_cast<unsigned*>(s_step + K);         // [K] tile base per label
+  unsigned* s_last = s_tb + K;                                      // [32] last label of each warp
+  unsigned* s_wc = s_last + 32;                                     // [32] contour bits per warp
+  uint16_t* s_wcnt = reinterpret_cast<uint16_t*>(s_wc + 32);        // [32][K] per-warp label counts -> offsets
+
+  const int f = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+  const unsigned lane = tid & 31, warp = tid >> 5;
+  for (int l = tid; l < K; l += kQThreads) {
+    s_model[l] = reinterpret_cast<const float4*>(model)[(size_t)f * K + l];
+    s_step[l] = step_per_label ? step_per_label[(size_t)f * K + l] : step;
+    s_tb[l] = bk.tile_off[((size_t)f * T + tile) * K + l];
+  }
+  for (int i = tid; i < 32 * K; i += kQThreads) s_wcnt[i] = 0;
+  __syncthreads();
+
+  const int p = tile * kQThreads + tid;
+  const bool inb = p < HW;
+  int label = 1;
+  int q = 0;
+  if (inb) {
+    label = labels[(size_t)f * HW + p];
+    if (label >= K) label = 1;  // flagged by label_stats; never emitted
+    const float r = range[(size_t)f * HW + p];
+    const float pred = predict_range(s_model[label], lut + (size_t)p * 3);
+    const float res = r - pred;
+    q = (int)roundf(res / s_step[label]);
+  }
+  const unsigned grp = __match_any_sync(0xffffffffu, label);
+  const unsigned rank_in_warp = __popc(grp & lanemask_lt());
+  if (rank_in_warp == 0) s_wcnt[warp * K + label] = (uint16_t)__popc(grp);
+  if (lane == 31) s_last[warp] = (unsigned)label;
+  __syncthreads();
+
+  // contour bit of this pixel (cpp_modules.cpp:534-545)
+  int left = __shfl_up_sync(0xffffffffu, label, 1);
+  if (lane == 0) left = warp > 0 ? (int)s_last[warp - 1] : (p > 0 && inb ? (int)labels[(size_t)f * HW + p - 1] : -1);
+  const bool cbit = inb && ((p % W) == 0 || label != left);
+  const unsigned cb = __ballot_sync(0xffffffffu, cbit);
+  if (lane == 0) s_wc[warp] = __popc(cb);
+  {
+    // MSB-first packing (np.packbits): pixel p0+i -> byte i/8, bit 7-(i%8)
+    const unsigned word = __byte_perm(__brev(cb), 0, 0x0123);
+    const int byte0 = (tile * kQThreads + (int)warp * 32) >> 3;
+    uint8_t* dst = contour_bits + (size_t)f * cbytes + byte0;
+    if ((cbytes & 3) == 0 && byte0 + 4 <= cbytes) {
+      if (lane == 0) *reinterpret_cast<unsigned*>(dst) = word;
+    } else if (lane < 4 && byte0 + (int)lane < cbytes) {
+      dst[lane] = (uint8_t)(word >> (8 * lane));
+    }
+  }
+  // per-label exclusive scan over the 32 warps: warp w owns labels w, w+32, ...
+  for (int l = warp; l < K; l += 32) {
+    const unsigned c = s_wcnt[lane * K + l];
+    unsigned incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (unsigned)o) incl += v;
+    }
+    s_wcnt[lane * K + l] = (uint16_t)(incl - c);
+  }
+  __syncthreads();
+
+  if (inb && label != 1) {
+    const unsigned pos = s_tb[label] + s_wcnt[warp * K + label] + rank_in_warp;
+    symbols[(size_t)f * sym_stride + pos] = (int16_t)q;
+  }
+  // idx_sequence position: contour bits before this pixel
+  {
+    const unsigned wc = s_wc[lane];
+    unsigned incl = wc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (unsigned)o) incl += v;
+    }
+    const unsigned before_warp = __shfl_sync(0xffffffffu, incl - wc, warp);
+    if (cbit) {
+      const unsigned pos = bk.tile_coff[(size_t)f * T + tile] + before_warp + __popc(cb & lanemask_lt());
+      seq[(size_t)f * seq_stride + pos] = (uint16_t)label;
+    }
+  }
+}
+
+}  // namespace rpcc
+
+using namespace rpcc;
+
+extern "C" int rpcc_quantize_pack_batch(const float* range, const uint8_t* labels, const float* model, const float* lut,
+                                        void* book, const float* step_per_label, float step, int B, int H, int W, int K,
+                                        int16_t* symbols, size_t sym_stride, uint8_t* contour_bits, uint16_t* seq,
+                                        size_t seq_stride, void* stream) {
+  RPCC_REQUIRE(range && labels && model && lut && book && symbols && contour_bits && seq, "null pointer");
+  RPCC_REQUIRE(K >= 2 && K <= 254, "K must be in [2, 254]");
+  RPCC_REQUIRE(B <= 65535, "at most 65535 frames per launch");
+  if (B == 0) return RPCC_OK;
+  const int HW = H * W, T = (HW + kQThreads - 1) / kQThreads;
+  const Book bk = make_book(book, B, T, K);
+  const size_t smem = (sizeof(float4) + sizeof(float) + sizeof(unsigned)) * K + sizeof(unsigned) * 64 +
+                      sizeof(uint16_t) * 32 * (size_t)K + 16;
+  quantize_pack_kernel<<<dim3(T, B), kQThreads, smem, as_stream(stream)>>>(
+      range, labels, model, lut, bk, step_per_label, step, HW, W, K, T, symbols, sym_stride, contour_bits,
+      (HW + 7) / 8, seq, seq_stride);
+  RPCC_LAUNCH_CHECK("quantize_pack_kernel");
+  return RPCC_OK;
+}

@@ -1,0 +1,213 @@
+"""GPU parity tests, stage by stage, through the C ABI (rpcc_*_batch) against the oracle
+(oracle/liborc.so), the reference's own compiled code (oracle/_ref, when shipped) and torch's own
+arithmetic for the segment() lines (tests/refimpl.py).  Integer/index/byte results: bit-exact."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import ref
+from conftest import EXAMPLE_GROUND
+
+pytestmark = pytest.mark.gpu
+
+LIDARS = ["Velodyne64E", "Velodyne32E", "VelodyneVLP16"]
+
+
+@pytest.fixture(scope="module")
+def T():
+    import torch
+    return torch
+
+
+@pytest.fixture(scope="module")
+def R():
+    import rpcc_b200
+    from rpcc_b200 import device, synthetic
+    rpcc_b200.device_mod = device
+    rpcc_b200.synth = synthetic
+    return rpcc_b200
+
+
+def _frames(R, lidar, seeds):
+    pts, off, g = R.synth.batch(seeds, lidar)
+    return pts, off, g
+
+
+def _project_dev(T, R, pts, off, lidar_name):
+    cfg = R.LidarConfig(lidar_name)
+    d_pts = T.from_numpy(pts).cuda()
+    d_off = T.from_numpy(off).cuda()
+    rng = R.device_mod.project_batch(d_pts, d_off, cfg)
+    T.cuda.synchronize()
+    return cfg, rng
+
+
+# ----------------------------------------------------------------------------- stage 1
+def test_project_example_bit_exact(T, R, example_points):
+    off = np.array([0, example_points.shape[0]], np.int64)
+    cfg, rng = _project_dev(T, R, example_points, off, "Velodyne64E")
+    H, W, hf, vmax, vmin = oracle.lidar_params("Velodyne64E")
+    want = oracle.project(example_points, H, W, hf, vmax, vmin)
+    got = rng[0].cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert (got != 0).sum() == 94053
+    if ref.have_cpp():
+        r = ref.cpp("dataset_utils_cpp").point_cloud_to_range_image_even(
+            np.ascontiguousarray(example_points[:, :3]), H, W, hf, vmax, vmin)
+        assert np.array_equal(got.view(np.uint32), r.view(np.uint32))
+
+
+@pytest.mark.parametrize("lidar", LIDARS)
+def test_project_synthetic_batch(T, R, lidar):
+    pts, off, _ = _frames(R, lidar, range(6))
+    cfg, rng = _project_dev(T, R, pts, off, lidar)
+    H, W, hf, vmax, vmin = oracle.lidar_params(lidar)
+    got = rng.cpu().numpy()
+    for b in range(6):
+        want = oracle.project(pts[off[b]:off[b + 1]], H, W, hf, vmax, vmin)
+        assert np.array_equal(got[b].view(np.uint32), want.view(np.uint32)), (lidar, b)
+
+
+def test_project_stride3_empty_and_zero_points(T, R):
+    cfg = R.LidarConfig("Velodyne64E")
+    H, W, hf, vmax, vmin = oracle.lidar_params("Velodyne64E")
+    p0, _ = R.synth.frame(3)
+    rs = np.random.default_rng(0)
+    # frame 1: exact-zero points sprinkled in (they re-open their pixel), frame 2: empty
+    p1 = p0[:5000].copy()
+    zrow = int(round((0 - np.float32(vmin)) / ((np.float32(vmax) - np.float32(vmin)) / 63)))
+    # points that land on the zero-depth pixel (row zrow, col 0), before and after the zeros
+    dirv = oracle.transform_map(H, W, hf, vmax, vmin)[zrow, 0]
+    hits = np.stack([dirv * d for d in (7.0, 5.0, 9.0, 8.0)]).astype(np.float32)
+    seqs = [hits[0], hits[1], np.zeros(3, np.float32), hits[2], np.array([-0.0, 0.0, 0.0], np.float32), hits[3]]
+    ins = sorted(rs.choice(5000, len(seqs), replace=False))
+    for i, s in zip(ins, seqs):
+        p1[i, :3] = s
+    frames = [p0[:, :3].copy(), p1[:, :3].copy(), np.zeros((0, 3), np.float32), p0[:100, :3].copy()]
+    pts = np.ascontiguousarray(np.concatenate(frames, 0))
+    off = np.cumsum([0] + [f.shape[0] for f in frames]).astype(np.int64)
+    rng = R.device_mod.project_batch(T.from_numpy(pts).cuda(), T.from_numpy(off).cuda(), cfg)
+    got = rng.cpu().numpy()
+    for b, fr in enumerate(frames):
+        want = oracle.project(fr, H, W, hf, vmax, vmin)
+        assert np.array_equal(got[b].view(np.uint32), want.view(np.uint32)), b
+    assert got[2].max() == 0
+
+
+# ----------------------------------------------------------------------------- torch semantics (H2)
+def test_torch_size3_reduction_association(T):
+    """Pins the float32 association of torch.sum / torch.norm over a size-3 last dim on this box:
+    the device kernels assume (t0 + t2) + t1 (common.cuh torch_sum3)."""
+    g = np.random.default_rng(7)
+    n = 1 << 22
+    v = (g.standard_normal((n, 3)) * g.uniform(0.01, 80, (n, 1))).astype(np.float32)
+    tv = T.from_numpy(v).cuda()
+    got_sum = T.sum(tv * tv, -1).cpu().numpy()
+    got_norm = T.norm(tv, 2, -1).cpu().numpy()
+    sq = v * v
+    a02_1 = (sq[:, 0] + sq[:, 2]) + sq[:, 1]
+    a01_2 = (sq[:, 0] + sq[:, 1]) + sq[:, 2]
+    m_sum = {"(0+2)+1": np.mean(got_sum != a02_1), "(0+1)+2": np.mean(got_sum != a01_2)}
+    m_norm = {"(0+2)+1": np.mean(got_norm != np.sqrt(a02_1)), "(0+1)+2": np.mean(got_norm != np.sqrt(a01_2))}
+    print("sum mismatch rates", m_sum, "norm mismatch rates", m_norm)
+    assert m_sum["(0+2)+1"] == 0.0, m_sum
+    assert m_norm["(0+2)+1"] == 0.0, m_norm
+    # 4-D broadcast shape used by calc_cluster_residual_radius (H,W,100,3) and the (1,1,3) plane norm
+    pc = tv[: 64 * 500].view(64, 500, 1, 3)
+    c = tv[100000:100100].view(1, 1, 100, 3)
+    d = T.norm(pc - c, 2, -1).cpu().numpy()
+    dn = (v[: 64 * 500].reshape(64, 500, 1, 3) - v[100000:100100].reshape(1, 1, 100, 3))
+    dq = dn * dn
+    assert np.array_equal(d, np.sqrt((dq[..., 0] + dq[..., 2]) + dq[..., 1]))
+    g3 = T.norm(tv[:1].view(1, 1, 3), 2, -1).cpu().numpy().ravel()[0]
+    assert g3 == np.sqrt((sq[0, 0] + sq[0, 2]) + sq[0, 1])
+    # comparison against the python scalar is done in float32; max returns the first index on ties
+    x = T.tensor([np.float32(0.1)], dtype=T.float32).cuda()
+    assert not bool((x > 0.1).item())
+    t = T.tensor([[-1.0, -1.0, -2.0, -1.0]]).cuda()
+    assert int(T.max(t, -1)[1].item()) == 0
+
+
+# ----------------------------------------------------------------------------- stage 2: FPS
+def test_fps_generic_vs_reference_kernel(T, R):
+    g = np.random.default_rng(1)
+    for n, m, dup in [(5000, 64, False), (1024, 32, True), (777, 20, True), (40000, 100, False), (33, 8, False)]:
+        pts = g.standard_normal((2, n, 3)).astype(np.float32) * 10
+        if dup:  # exact ties: many identical points (the masked origin points of segment())
+            pts[:, g.choice(n, n // 2, replace=False)] = 0.0
+            pts[1, :, :] = np.round(pts[1], 0)
+        got = R.device_mod.fps_batch(T.from_numpy(pts).cuda(), m).cpu().numpy()
+        for b in range(2):
+            want = oracle.fps(pts[b], m)
+            assert np.array_equal(got[b], want), (n, m, b)
+        if ref.have_cuda():
+            import refimpl
+            r = refimpl.ref_fps_gpu(T.from_numpy(pts).cuda(), m).cpu().numpy()
+            assert np.array_equal(got, r), (n, m)
+
+
+@pytest.mark.parametrize("lidar", LIDARS)
+def test_segment_fps_and_labels(T, R, lidar):
+    import refimpl
+    seeds = [0, 1, 2]
+    pts, off, grounds = _frames(R, lidar, seeds)
+    cfg, rng = _project_dev(T, R, pts, off, lidar)
+    lut = cfg.transform_map()
+    d_lut = T.from_numpy(lut).cuda()
+    d_g = T.from_numpy(grounds.astype(np.float32)).cuda()
+    cidx, centers = R.device_mod.segment_fps_batch(rng, d_lut, d_g, 100, 0.1)
+    labels, book = R.device_mod.assign_labels_batch(rng, d_lut, d_g, centers)
+    T.cuda.synchronize()
+    ri = rng.cpu().numpy()
+    for b in range(len(seeds)):
+        seg_o, cidx_o, cent_o = oracle.segment(ri[b], lut, grounds[b], 100)
+        seg_t, cidx_t, ng_t = refimpl.torch_segment(ri[b], lut, grounds[b], 100)
+        # the oracle restatement and torch's own arithmetic (+ the reference FPS kernel) agree ...
+        assert np.array_equal(cidx_o, cidx_t), (lidar, b)
+        assert np.array_equal(seg_o, seg_t), (lidar, b, int((seg_o != seg_t).sum()))
+        # ... and the device path reproduces both
+        assert np.array_equal(cidx[b].cpu().numpy(), cidx_t), (lidar, b)
+        assert np.array_equal(centers[b].cpu().numpy(), ng_t[cidx_t]), (lidar, b)
+        assert np.array_equal(labels[b].cpu().numpy().astype(np.int64), seg_t), (lidar, b)
+
+
+def test_segment_example_frame(T, R, example_points):
+    import refimpl
+    off = np.array([0, example_points.shape[0]], np.int64)
+    cfg, rng = _project_dev(T, R, example_points, off, "Velodyne64E")
+    lut = cfg.transform_map()
+    d_lut = T.from_numpy(lut).cuda()
+    d_g = T.tensor([EXAMPLE_GROUND], dtype=T.float32).cuda()
+    cidx, centers = R.device_mod.segment_fps_batch(rng, d_lut, d_g, 100, 0.1)
+    labels, _ = R.device_mod.assign_labels_batch(rng, d_lut, d_g, centers)
+    seg_t, cidx_t, _ = refimpl.torch_segment(rng[0].cpu().numpy(), lut, np.array(EXAMPLE_GROUND), 100)
+    assert np.array_equal(cidx[0].cpu().numpy(), cidx_t)
+    assert np.array_equal(labels[0].cpu().numpy().astype(np.int64), seg_t)
+
+
+# ----------------------------------------------------------------------------- stages 3+4
+@pytest.mark.parametrize("lidar", LIDARS)
+def test_model_quantize_pack(T, R, lidar):
+    seeds = [4, 5]
+    pts, off, grounds = _frames(R, lidar, seeds)
+    cfg, rng = _project_dev(T, R, pts, off, lidar)
+    lut = cfg.transform_map()
+    d_lut = T.from_numpy(lut).cuda()
+    d_g = T.from_numpy(grounds.astype(np.float32)).cuda()
+    cidx, centers = R.device_mod.segment_fps_batch(rng, d_lut, d_g, 100, 0.1)
+    labels, book = R.device_mod.assign_labels_batch(rng, d_lut, d_g, centers)
+    model, results = R.device_mod.point_model_batch(rng, labels, d_g, book, 102)
+    step = 0.04
+    symbols, contour, seq = R.device_mod.quantize_pack_batch(rng, labels, model, d_lut, book, step)
+    T.cuda.synchronize()
+    res = results.cpu().numpy().view(np.uint32)
+    for b in range(len(seeds)):
+        want = oracle.compress_frame(pts[off[b]:off[b + 1]], lidar, grounds[b])
+        sec = want["sections"]
+        nsym, nseq, rows = int(res[b, 0]), int(res[b, 1]), int(res[b, 2])
+        assert np.array_equal(labels[b].cpu().numpy().astype(np.int32), want["seg_idx"])
+        assert rows == want["model_param"].shape[0]
+        assert model[b, :rows].cpu().numpy().tobytes() == sec["plane_param"]
+        assert symbols[b, :nsym].cpu().numpy().tobytes() == sec["residual_quantized"]
+        assert contour[b].cpu().numpy().tobytes() == sec["contour_map"]
+        assert seq[b, :nseq].cpu().numpy().tobytes() == sec["idx_sequence"]
