@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of R-PCC's per-frame compression hot path on synthetic KITTI-like 64E frames.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one pass of project -> ground fit -> FPS -> labels -> point models -> quantise + pack
+over `--frames` frames per GPU (BASELINE.json configs[1]/[4]: Velodyne64E, FPS + point modelling,
+accuracy 0.02, ~120k points per frame).  `value` is measured with the points already resident in
+HBM; `e2e` goes through rpcc_encoder_encode_host with pinned host buffers (upload + kernels +
+download inside the timed region).  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "64E frames/sec (project->FPS->model->quantize)"
+UNIT = "frames/s"
+LIDAR = "Velodyne64E"
+HW = 64 * 2000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=1024, help="frames per step per GPU")
+    ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic frames generated per GPU")
+    ap.add_argument("--max-batch", type=int, default=256, help="frames per kernel launch")
+    ap.add_argument("--e2e-frames", type=int, default=512)
+    ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.stop = False
+        self.index = index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------- workload
+def make_workload(distinct, frames, rank):
+    """`distinct` generated frames tiled to `frames` slots (each slot is its own copy in memory, so
+    every frame of a step is read from HBM; the per-step input is ~2 GB, far larger than L2)."""
+    from rpcc_b200 import synthetic
+    seeds = [rank * 100000 + i for i in range(distinct)]
+    per = [synthetic.frame(s, LIDAR) for s in seeds]
+    pts, grounds, off = [], [], [0]
+    for i in range(frames):
+        p, g = per[i % distinct]
+        pts.append(p)
+        grounds.append(g)
+        off.append(off[-1] + p.shape[0])
+    return np.concatenate(pts, 0), np.asarray(off, np.int64), np.stack(grounds).astype(np.float32)
+
+
+def cpu_oracle_frame(args):
+    """One frame through the CPU path: the reference's compiled C++ (oracle/_ref) for the stages it
+    has on the CPU, the oracle's C restatement for segment() (GPU-only in the reference)."""
+    import oracle
+    from oracle import ref
+    pts, ground, use_ref = args
+    H, W, hf, vmax, vmin = oracle.lidar_params(LIDAR)
+    lut = cpu_oracle_frame.lut
+    if use_ref:
+        d, s, q, c = (ref.cpp("dataset_utils_cpp"), ref.cpp("segment_utils_cpp"), ref.cpp("quantization_utils_cpp"),
+                      ref.cpp("contour_utils_cpp"))
+        ri = d.point_cloud_to_range_image_even(np.ascontiguousarray(pts[:, :3]), H, W, hf, vmax, vmin)
+        seg, _, _ = oracle.segment(ri, lut, ground, 100)
+        pm = s.point_modeling(ri[..., None], seg)
+        cm = np.concatenate((np.zeros((pm.shape[0], 3)), pm[:, None]), -1)[1:]
+        mp = np.concatenate((np.asarray(ground, np.float64).reshape(1, 4), cm), 0)
+        pred = s.intra_predict(seg, mp, lut)
+        res = ri[..., None] - pred
+        sym = q.uniform_quantize(seg, res, 0.04)
+        c.extract_contour(seg)
+        return int(sym.size)
+    out = oracle.compress_frame(pts, LIDAR, ground)
+    return int(out["symbols"].size)
+
+
+def _cpu_init():
+    import oracle
+    H, W, hf, vmax, vmin = oracle.lidar_params(LIDAR)
+    cpu_oracle_frame.lut = oracle.transform_map(H, W, hf, vmax, vmin)
+
+
+def cpu_throughput(n_frames, cores, use_ref):
+    """frames/s of the CPU path on `cores` processes over a bounded sample of the workload."""
+    import multiprocessing as mp
+    from rpcc_b200 import synthetic
+    frames = [synthetic.frame(900000 + i, LIDAR) for i in range(min(n_frames, 32))]
+    jobs = [(frames[i % len(frames)][0], frames[i % len(frames)][1], use_ref) for i in range(n_frames)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_cpu_init) as pool:
+        pool.map(cpu_oracle_frame, jobs[:cores])  # warm the workers
+        t0 = time.perf_counter()
+        pool.map(cpu_oracle_frame, jobs, chunksize=1)
+        dt = time.perf_counter() - t0
+    return n_frames / dt, dt
+
+
+def reference_arm(a):
+    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from oracle import ref
+    oracle.lib()
+    use_ref = ref.have_cpp()
+    cores = os.cpu_count() or 1
+    per_step = max(cores * 2, 8)
+    for _ in range(a.warmup):
+        cpu_throughput(cores, cores, use_ref)
+    t_all, n_all = 0.0, 0
+    for _ in range(a.steps):
+        fps, dt = cpu_throughput(per_step, cores, use_ref)
+        t_all += dt
+        n_all += per_step
+    value = n_all / t_all
+    kind = "reference" if use_ref else "port"
+    sample = ("%d synthetic 64E frames per step on %d host processes; projection, point_modeling, intra_predict, "
+              "uniform_quantize, extract_contour = %s; segment() (mask + FPS + label assignment, GPU-only in the "
+              "reference) = oracle C restatement; ground model injected; no entropy coder" %
+              (per_step, cores, "the reference's own C++ (oracle/_ref)" if use_ref else "oracle C restatement"))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1000.0 * t_all / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "Velodyne64E uniform, FPS(100) + point modelling, accuracy 0.02, ~120k points/frame",
+                       "frames_per_step": per_step},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------- main arm
+def main():
+    a = parse()
+    if a.impl == "reference":
+        reference_arm(a)
+        return
+    import torch
+    import torch.distributed as dist
+
+    import rpcc_b200
+    from rpcc_b200.batch import BatchEncoder
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    F, MB = a.frames, min(a.max_batch, a.frames)
+    pts_np, off_np, g_np = make_workload(a.distinct, F, rank)
+    npts = int(off_np[-1])
+    max_chunk_pts = int(max(off_np[min(i + MB, F)] - off_np[i] for i in range(0, F, MB)))
+    enc = BatchEncoder(LIDAR, accuracy=0.02, max_batch=MB, max_points=max_chunk_pts, device=local)
+    d_pts = torch.from_numpy(pts_np).cuda()
+    d_off = torch.from_numpy(off_np).cuda()
+    d_g = torch.from_numpy(g_np).cuda()
+    chunks = [(i, min(MB, F - i)) for i in range(0, F, MB)]
+    nslots = enc.slots
+    streams = [torch.cuda.ExternalStream(enc.stream(s)) for s in range(nslots)]
+
+    def step():
+        for ci, (f0, nb) in enumerate(chunks):
+            # un-rebased offsets: the kernel indexes `points` with absolute row numbers
+            enc.encode_device(ci % nslots, d_pts, d_off[f0:f0 + nb + 1], nb, d_g[f0:f0 + nb])
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    enc.sync()
+    torch.cuda.synchronize()
+    barrier()
+
+    launches0 = rpcc_b200.launch_count()
+    enc.profile(True)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(nslots)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(nslots)]
+    with ClockSampler(local) as clk:
+        torch.cuda.synchronize()
+        barrier()
+        for s in range(nslots):
+            starts[s].record(streams[s])
+        for _ in range(a.steps):
+            step()
+        for s in range(nslots):
+            ends[s].record(streams[s])
+        enc.sync()
+        torch.cuda.synchronize()
+        barrier()
+    elapsed_ms = max(starts[i].elapsed_time(ends[j]) for i in range(nslots) for j in range(nslots))
+    launches = rpcc_b200.launch_count() - launches0
+    stage_ms, stage_frames, stage_calls = enc.stage_times()
+    enc.profile(False)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = world * F * a.steps / (elapsed_ms / 1000.0)
+
+    # ---- e2e: host buffers through the C ABI (upload + kernels + download inside the timed region)
+    e2e = None
+    if not a.no_e2e:
+        EF = min(a.e2e_frames, F)
+        h_pts = torch.from_numpy(pts_np[:off_np[EF]]).pin_memory()
+        h_off = off_np[:EF + 1].copy()
+        h_g = g_np[:EF].copy()
+        out = enc.encode_host(h_pts, h_off, h_g)  # warm-up (allocates the pinned output buffers)
+        d2h = int(out["symbols"].nbytes + out["seq"].nbytes + out["model"].nbytes + out["contour"].nbytes + 16 * EF)
+        h2d = int(h_pts.numel() * 4 + h_off.nbytes + h_g.nbytes)
+        enc.encode_host(h_pts, h_off, h_g)
+        torch.cuda.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(2, a.steps)
+        e0.record()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            enc.encode_host(h_pts, h_off, h_g)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ev_ms = e0.elapsed_time(e1)
+        t2 = torch.tensor([max(ev_ms / 1000.0, wall)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e_fps = world * EF * reps / float(t2.item())
+        # full .rpcc including the host bz2 threads, reported beside (not the headline metric)
+        t0 = time.perf_counter()
+        blobs = enc.compress(h_pts[:off_np[min(EF, 128)]], off_np[:min(EF, 128) + 1].copy(), g_np[:min(EF, 128)].copy())
+        rpcc_fps = min(EF, 128) / (time.perf_counter() - t0)
+        e2e = {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "frames_per_step": EF, "with_host_bz2_frames_per_s": rpcc_fps, "host_threads": enc.workers,
+               "mean_rpcc_bytes": float(np.mean([len(b) for b in blobs]))}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline: algorithmic bytes (SURVEY 8d / DESIGN.md) over the live per-stage event times
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    n_mean = npts / F
+    valid_mean = float(HW * 0.78)
+    try:
+        res = enc.device_buffer(0, "results", (MB, 4), torch.int32).cpu().numpy()
+        valid_mean = float(res[:, 0].astype(np.int64).mean())
+        runs_mean = float(res[:, 1].astype(np.int64).mean())
+    except Exception:
+        runs_mean = 30000.0
+    alg = {  # bytes per frame
+        "project": 16.0 * n_mean + 4.0 * HW,
+        "quantize": 4.0 * HW + 1.0 * HW + 2.0 * valid_mean + HW / 8.0 + 2.0 * runs_mean,
+        "assign": 4.0 * HW + 1.0 * HW,
+        "fps": 4.0 * HW,
+    }
+    total_stage = sum(stage_ms.values()) or 1.0
+    kernels = {}
+    for k, ms in stage_ms.items():
+        if ms <= 0:
+            continue
+        ent = {"ms_per_launch": ms / max(stage_calls, 1), "share_of_step": ms / total_stage,
+               "frames_per_launch": stage_frames / max(stage_calls, 1)}
+        if k in alg:
+            gbs = alg[k] * stage_frames / (ms / 1000.0) / 1e9
+            ent.update({"algorithmic_bytes_per_frame": alg[k], "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak})
+        kernels[k] = ent
+    pj = kernels.get("project", {})
+    roofline = {"kernel": "project_kernel", "bound": "hbm", "achieved": pj.get("achieved_gbs"), "peak": peak,
+                "unit": "GB/s", "frac": pj.get("frac_of_hbm_peak"), "traffic": None, "peak_source": peak_src,
+                "note": "dominant HBM mover of the chain (16 B/point in + 4 B/pixel out); the chain's time is dominated by "
+                        "the latency/issue-bound FPS and label kernels, see kernels{}", "kernels": kernels}
+
+    cpu_baseline = None
+    if not a.no_cpu_baseline:
+        import oracle
+        from oracle import ref
+        use_ref = ref.have_cpp()
+        cores = os.cpu_count() or 1
+        n = a.cpu_frames or max(2 * cores, 16)
+        fps, dt = cpu_throughput(n, cores, use_ref)
+        cpu_baseline = {"value": fps, "unit": UNIT, "cores": cores, "kind": "reference" if use_ref else "port",
+                        "sample": "%d frames of the same synthetic 64E workload in %.1f s on %d host processes (%s for the CPU "
+                                  "stages; oracle C restatement of the GPU-only segment(); no entropy coder)" %
+                                  (n, dt, cores, "reference C++ from oracle/_ref" if use_ref else "oracle C restatement")}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "Velodyne64E uniform, FPS(100) + point modelling, accuracy 0.02 (BASELINE configs[1]/[4] frame "
+                                   "shape), %.0f points/frame" % n_mean,
+                       "frames_per_step_per_gpu": F, "frames_per_launch": MB, "distinct_frames": a.distinct,
+                       "l2": "inputs larger than L2 (%.2f GB of points per step)" % (npts * 16 / 1e9),
+                       "ground_model": "injected (true plane of the synthetic scene)"},
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu_baseline}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -71,11 +71,12 @@ RPCC_API int rpcc_project_batch(const float* points, int stride, const int64_t* 
 /* a3. dataset/transformer.py:94-101 range_image_to_point_cloud: xyz[b][h][w][3] = range * lut. */
 RPCC_API int rpcc_range_to_xyz_batch(const float* range, const float* lut, int B, int HW, float* xyz, void* stream);
 
-/* a4 (first half). deterministic ground plane fit replacing open3d segment_plane
- * (utils/segment_utils.py:74-82,101-108).  ground: [B][4] f32 unit-normal plane. */
-RPCC_API int rpcc_ground_fit_batch(const float* range, const float* lut, int B, int H, int W,
-                          uint64_t seed, float* ground, void* workspace, size_t workspace_bytes, void* stream);
-RPCC_API size_t rpcc_ground_fit_workspace(int B, int H, int W);
+/* a4 (first half). Deterministic ground-plane RANSAC standing in for open3d segment_plane
+ * (utils/segment_utils.py:74-82,101-108; parity unpinned, see ground.cu).  Frame b of the batch is
+ * keyed by (seed + b), so a frame's plane does not depend on how frames are batched if the caller
+ * passes seed = base + index of the first frame.  ground: [B][4] f32, unit normal. */
+RPCC_API int rpcc_ground_fit_batch(const float* range, const float* lut, int B, int H, int W, uint64_t seed,
+                          float* ground, void* stream);
 
 /* a5. ops/fps/src/sampling_gpu.cu:24-184 furthest_point_sampling_kernel_launcher.
  * points [B][n][3] f32 -> idx [B][m] i32.  Same seeds as the reference kernel, including its
@@ -120,37 +121,65 @@ RPCC_API int rpcc_point_model_batch(const float* range, const uint8_t* labels, c
  * per-label steps), :521-558 extract_contour + np.packbits, fused.  step_per_label: NULL =>
  * uniform `step`; else [B][K] f32.  symbols: [B][sym_stride] i16 (first sym_count[b] valid),
  * label-major / raster-within-label.  contour_bits [B][ceil(HW/8)] u8 MSB-first;
- * seq [B][seq_stride] u16 (first seq_count[b] valid).  `book` must have been through
- * rpcc_point_model_batch (or rpcc_book_offsets_batch). */
+ * seq [B][seq_stride] u16 (first seq_count[b] valid); with sym_base / seq_base non-NULL frame b's
+ * streams start at symbols + sym_base[b] / seq + seq_base[b] instead.  `book` must have been
+ * through rpcc_point_model_batch. */
 RPCC_API int rpcc_quantize_pack_batch(const float* range, const uint8_t* labels, const float* model, const float* lut,
                              void* book, const float* step_per_label, float step, int B, int H, int W, int K,
                              int16_t* symbols, size_t sym_stride, uint8_t* contour_bits, uint16_t* seq,
-                             size_t seq_stride, void* stream);
+                             size_t seq_stride, const uint64_t* sym_base, const uint64_t* seq_base, void* stream);
+
+/* Exclusive scan of results[b].sym_count / seq_count into sym_base / seq_base ([B+1] u64, device;
+ * entry B = totals): pass them to rpcc_quantize_pack_batch to get the frames' streams packed back
+ * to back instead of strided. */
+RPCC_API int rpcc_frame_offsets_batch(const rpcc_frame_result* results, int B, uint64_t* sym_base, uint64_t* seq_base,
+                             void* stream);
 
 /* a9. cpp_modules.cpp:28-121 extract_features_with_segment (+:10-25) and the salience rule of
- * :388-405.  key_points [B][HW] u8 (0..3); salience [B][K] u8; step_per_label [B][K] f32. */
-RPCC_API int rpcc_keypoints_salience_batch(const float* range, const uint8_t* labels, const uint32_t* label_cnt,
-                                  int B, int H, int W, int K, int region, int segments, int sharp_num,
-                                  int less_sharp_num, int flat_num, const int32_t* level_kp_num,
-                                  const float* level_acc, int level_num, int ground_level,
-                                  uint8_t* key_points, uint8_t* salience, float* step_per_label, void* stream);
+ * :388-405.  key_points [B][HW] u8 (0..3); feat [B][HW] f32 curvature map or NULL;
+ * salience [B][K] u8 and step_per_label [B][K] f32 (both NULL => key points only);
+ * level tables are HOST arrays (<= 8 levels); kp_cnt: u32 [B][K] device scratch.
+ * `book` must hold the label counts (rpcc_assign_labels_batch / rpcc_label_stats_batch). */
+RPCC_API int rpcc_keypoints_salience_batch(const float* range, const uint8_t* labels, const void* book, int B, int H, int W,
+                                  int K, int region, int segments, int sharp_num, int less_sharp_num, int flat_num,
+                                  const int32_t* level_kp_num, const float* level_acc, int level_num,
+                                  int ground_level, uint8_t* key_points, float* feat, uint8_t* salience,
+                                  float* step_per_label, uint32_t* kp_cnt, void* stream);
 
 /* a11. decode: cpp_modules.cpp:561-593 recover_map, utils/compress_utils.py:114-132
- * dequantize_residual, cpp_modules.cpp:248-285 intra_predict, dataset/transformer.py:94-101.
- * contour_bits [B][ceil(HW/8)], seq [B][seq_stride] u16, symbols [B][sym_stride] i16,
- * model [B][K][4]; steps [B][K] f64 (per-label dequantisation step).
- * Outputs: labels [B][HW] u8, range_rec [B][HW] f32, xyz [B][HW][3] f32 (may be NULL). */
-RPCC_API int rpcc_decode_batch(const uint8_t* contour_bits, const uint16_t* seq, int seq_stride, const int16_t* symbols,
-                      int sym_stride, const float* model, const double* steps, const float* lut,
-                      int B, int H, int W, int K, uint8_t* labels, float* range_rec, float* xyz,
-                      void* workspace, size_t workspace_bytes, void* stream);
-RPCC_API size_t rpcc_decode_workspace(int B, int H, int W, int K);
+ * dequantize_residual, cpp_modules.cpp:248-285 intra_predict, tools/decompress.py:108-110,
+ * dataset/transformer.py:94-101.
+ * contour_bits [B][ceil(HW/8)], seq [B][seq_stride] u16 (seq_count [B] valid entries, or NULL =
+ * trusted), symbols [B][sym_stride] i16 (sym_count [B] or NULL), model [B][K][4] f32,
+ * steps [B][K] f64 (per-label dequantisation step: 2*accuracy, or the salience level's step).
+ * Outputs: labels [B][HW] u8, range_rec [B][HW] f32, xyz [B][HW][3] f32 (may be NULL),
+ * results [B]: symbols / sequence entries a well-formed stream of these labels holds (compare with
+ * the section lengths), flags bit1/bit2 on malformed input.  book: rpcc_book_bytes(B,H,W,K). */
+RPCC_API int rpcc_decode_batch(const uint8_t* contour_bits, const uint16_t* seq, size_t seq_stride,
+                      const uint32_t* seq_count, const int16_t* symbols, size_t sym_stride,
+                      const uint32_t* sym_count, const float* model, const double* steps, const float* lut,
+                      int B, int H, int W, int K, uint8_t* labels, float* range_rec, float* xyz, void* book,
+                      rpcc_frame_result* results, void* stream);
+
+/* Second half of decoding when the labels are already known; also the batched
+ * QuantizationModule.dequantize_residual (utils/compress_utils.py:114-132).  With a zero model and
+ * xyz = NULL, range_rec is the dequantised residual itself.  stats_ready = 0 unless `book` already
+ * holds this batch's label histograms. */
+RPCC_API int rpcc_dequantize_batch(const uint8_t* labels, const int16_t* symbols, size_t sym_stride,
+                          const uint32_t* sym_count, const float* model, const double* steps, const float* lut,
+                          int B, int H, int W, int K, float* range_rec, float* xyz, void* book,
+                          rpcc_frame_result* results, int stats_ready, void* stream);
 
 /* a12. chamfer3D.cu:12-154 NmDistanceKernel both ways: for each point of xyz1 [n][3] the squared
  * distance to and index of its nearest neighbour in xyz2 [m][3], and vice versa.  Exact brute
- * force, first-minimum tie rule as the reference. */
+ * force with the reference's FMA pattern and first-minimum tie rule.
+ * scratch: (n + m) * 8 bytes of device memory.  An empty cloud on the other side yields +inf / INT_MAX. */
 RPCC_API int rpcc_chamfer_batch(const float* xyz1, int n, const float* xyz2, int m, float* dist1, int32_t* idx1,
-                       float* dist2, int32_t* idx2, void* stream);
+                       float* dist2, int32_t* idx2, void* scratch, void* stream);
+/* utils/evaluate_metrics.py:20-22 + fscore.py:12-16 reductions: stats (device, 4 doubles) =
+ * {sum sqrt(dist1), #(dist1 < threshold_sq), sum sqrt(dist2), #(dist2 < threshold_sq)}. */
+RPCC_API int rpcc_chamfer_stats(const float* dist1, int n, const float* dist2, int m, float threshold_sq, double* stats,
+                       void* stream);
 
 /* ================================ host (numpy-facing) ops ==================================== */
 /* One frame, host pointers, synchronous; argument meaning follows the reference's pybind
@@ -166,10 +195,11 @@ RPCC_API int rpcc_op_intra_predict(const int32_t* seg, const float* model, int K
 /* quantization_utils_cpp.uniform_quantize (cpp_modules.cpp:288): out cap >= H*W; *n_out. */
 RPCC_API int rpcc_op_uniform_quantize(const int32_t* seg, const float* residual, int H, int W, float acc,
                              int32_t* out, int64_t* n_out);
-/* feature_extractor_cpp.extract_features_with_segment (cpp_modules.cpp:28) -> key_point_map */
+/* feature_extractor_cpp.extract_features_with_segment (cpp_modules.cpp:28) -> (feature_map [H][W] f32
+ * or NULL, key_point_map [H][W] i32); both zero where the reference leaves them unwritten. */
 RPCC_API int rpcc_op_extract_features_with_segment(const float* range, const int32_t* seg, int H, int W, int region,
                                           int segments, int sharp_num, int less_sharp_num, int flat_num,
-                                          int32_t* key_point_map);
+                                          float* feature_map, int32_t* key_point_map);
 /* quantization_utils_cpp.nonuniform_quantize (cpp_modules.cpp:337) */
 RPCC_API int rpcc_op_nonuniform_quantize(const int32_t* seg, const float* residual, const int32_t* key_point_map,
                                 int H, int W, const int32_t* level_kp_num, const float* level_acc, int level_num,
@@ -187,6 +217,15 @@ RPCC_API int rpcc_op_segment(const float* range, const float* lut, const float* 
 /* chamfer_3D.forward (chamfer_cuda.cpp:17) with host arrays, B = 1. */
 RPCC_API int rpcc_op_chamfer(const float* xyz1, int n, const float* xyz2, int m, float* dist1, int32_t* idx1,
                     float* dist2, int32_t* idx2);
+
+/* PCTransformer.range_image_to_point_cloud (dataset/transformer.py:94-101) with host arrays. */
+RPCC_API int rpcc_op_range_to_xyz(const float* range, const float* lut, int H, int W, float* xyz);
+/* The ground-plane fit of PointCloudSegment.segment (utils/segment_utils.py:101-108), host arrays. */
+RPCC_API int rpcc_op_ground_fit(const float* range, const float* lut, int H, int W, uint64_t seed, float* ground_out);
+/* QuantizationModule.dequantize_residual (utils/compress_utils.py:114-132): symbols (n,) i16, seg (H,W)
+ * i32, steps [K] f64 (one per label) -> residual (H,W) f32; *consumed = symbols the label map needs. */
+RPCC_API int rpcc_op_dequantize(const int16_t* symbols, int64_t n, const int32_t* seg, int H, int W, const double* steps,
+                       int K, float* residual_out, int64_t* consumed);
 
 /* ================================ batched encoder / decoder =================================== */
 typedef struct rpcc_encoder rpcc_encoder;
@@ -209,25 +248,38 @@ typedef struct rpcc_encoder_config {
 
 RPCC_API int rpcc_encoder_create(const rpcc_encoder_config* cfg, rpcc_encoder** out);
 RPCC_API void rpcc_encoder_destroy(rpcc_encoder* enc);
-/* Device-resident inputs (bench `value`): points/offsets as rpcc_project_batch; ground_in NULL =>
- * fitted on device, else [B][4] f32 device.  Results stay in the encoder's device buffers
- * (rpcc_encoder_device_buffers).  Enqueues on the encoder's stream; no sync. */
-RPCC_API int rpcc_encoder_encode_device(rpcc_encoder* enc, const float* points, int stride, const int64_t* offsets,
-                               int B, const float* ground_in);
-/* Host inputs/outputs (bench `e2e`, and what tools/compress_datalist.py would call): copies
- * points H2D from `points_host` (pinned or pageable), runs the chain, copies the sections back:
- *   results [B]; model [B][K][4] f32; contour_bits [B][ceil(HW/8)]; seq packed (sum seq_count) u16;
- *   symbols packed (sum sym_count) i16; salience [B][K] u8 (non-uniform, else may be NULL).
- * Synchronous.  ground_host NULL => fitted on device. */
+/* The encoder owns rpcc_encoder_slots() independent stream slots, each with buffers for max_batch
+ * frames; results of a call stay in its slot until the slot is used again. */
+RPCC_API int rpcc_encoder_slots(void);
+/* Device-resident inputs (bench `value`): points/offsets as rpcc_project_batch (device pointers),
+ * B <= max_batch; ground_in NULL => fitted on device, else [B][4] f32 (device or pinned host).
+ * Enqueues the whole chain on the slot's stream; no synchronisation. */
+RPCC_API int rpcc_encoder_encode_device(rpcc_encoder* enc, int slot, const float* points, int stride,
+                               const int64_t* offsets, int B, const float* ground_in);
+/* Host inputs/outputs (bench `e2e`, and what tools/compress_datalist.py calls): any B; frames are
+ * cut into chunks of max_batch and pipelined over the slots (upload / kernels / download overlap).
+ *   in : points_host rows of `stride` floats, offsets_host [B+1], ground_host [B][4] or NULL (fit on device)
+ *   out: results [B]; model [B][K][4] f32; contour_bits [B][ceil(HW/8)]; seq: every frame's
+ *        idx_sequence back to back (sum seq_count u16, capacity seq_cap entries); symbols likewise
+ *        (sum sym_count i16, capacity sym_cap); salience [B][K] u8 (non-uniform; may be NULL).
+ * Pinned host buffers make the copies asynchronous.  Synchronous: returns when everything is on the host. */
 RPCC_API int rpcc_encoder_encode_host(rpcc_encoder* enc, const float* points_host, int stride, const int64_t* offsets_host,
                              int B, const float* ground_host, rpcc_frame_result* results, float* model,
                              uint8_t* contour_bits, uint16_t* seq, size_t seq_cap, int16_t* symbols,
                              size_t sym_cap, uint8_t* salience);
 RPCC_API int rpcc_encoder_sync(rpcc_encoder* enc);
-RPCC_API void* rpcc_encoder_stream(rpcc_encoder* enc);
-/* Named device buffers of the last encode (for tests): "range","labels","model","symbols","seq",
- * "contour","results","center_idx","ground","key_points","salience". Returns NULL if unknown. */
-RPCC_API void* rpcc_encoder_device_buffer(rpcc_encoder* enc, const char* name);
+/* Per-stage device timing with CUDA events recorded on the slots' own streams between the stages of
+ * every chain call (at most 256 calls per slot are kept).  rpcc_encoder_profile(enc, 1) starts a fresh
+ * recording, (enc, 0) stops it.  rpcc_encoder_stage_times synchronises and returns the summed
+ * milliseconds of the 7 stages {project, ground, fps, assign, keypoints, model, quantize}, the frames
+ * they cover and the number of chain calls. */
+RPCC_API int rpcc_encoder_profile(rpcc_encoder* enc, int enable);
+RPCC_API int rpcc_encoder_stage_times(rpcc_encoder* enc, double* ms_out, long long* frames_out, int* calls_out);
+RPCC_API void* rpcc_encoder_stream(rpcc_encoder* enc, int slot);
+/* Named device buffers of a slot (tests, chaining): "range","labels","model","symbols","seq","contour",
+ * "results","center_idx","centers","ground","key_points","salience","step_per_label","sym_base",
+ * "seq_base","lut","points","offsets".  NULL if unknown / not allocated. */
+RPCC_API void* rpcc_encoder_device_buffer(rpcc_encoder* enc, int slot, const char* name);
 
 #ifdef __cplusplus
 }

@@ -35,7 +35,6 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         for name, rt in (("rpcc_last_error", C.c_char_p), ("rpcc_launch_count", C.c_longlong),
                          ("rpcc_encoder_stream", C.c_void_p), ("rpcc_encoder_device_buffer", C.c_void_p),
-                         ("rpcc_ground_fit_workspace", C.c_size_t), ("rpcc_decode_workspace", C.c_size_t),
                          ("rpcc_book_bytes", C.c_size_t)):
             try:
                 getattr(_lib, name).restype = rt

@@ -25,63 +25,6 @@ namespace rpcc {
 
 constexpr int kTile = RPCC_TILE;  // 1024 threads, one pixel each
 
-// One warp-level pass per distinct label in the warp: count + exact range sum into shared bins.
-__device__ __forceinline__ void warp_label_stats(int label, bool active, float r, unsigned* s_cnt,
-                                                 unsigned long long* s_sum, unsigned* s_flag) {
-  const unsigned lane = threadIdx.x & 31;
-  unsigned todo = __ballot_sync(0xffffffffu, active);
-  const bool exact = !(active && label >= 2) || (r >= 0.03125f && r < 256.0f);
-  if (__any_sync(0xffffffffu, !exact) && lane == 0) atomicOr(s_flag, 1u);
-  const unsigned long long v = active ? (unsigned long long)((double)r * 268435456.0) : 0ull;
-  while (todo) {
-    const int leader = __ffs(todo) - 1;
-    const int l = __shfl_sync(0xffffffffu, label, leader);
-    const bool mine = active && label == l;
-    const unsigned grp = __ballot_sync(0xffffffffu, mine);
-    // v < 2^36: split so that 32 addends cannot overflow 32 bits
-    const unsigned lo = mine ? (unsigned)(v & 0xFFFFFu) : 0u;
-    const unsigned hi = mine ? (unsigned)(v >> 20) : 0u;
-    const unsigned slo = __reduce_add_sync(0xffffffffu, lo);
-    const unsigned shi = __reduce_add_sync(0xffffffffu, hi);
-    if (lane == (unsigned)leader) {
-      atomicAdd(&s_cnt[l], (unsigned)__popc(grp));
-      if (l >= 2) atomicAdd(&s_sum[l], ((unsigned long long)shi << 20) + slo);
-    }
-    todo &= ~grp;
-  }
-}
-
-// Contour bits inside the tile (extract_contour, cpp_modules.cpp:534-545): a pixel starts a run when
-// it is in column 0 or its label differs from its left neighbour.  The tile's first pixel needs the
-// previous tile's last label, so it is left to model.cu; everything else is counted here.
-__device__ __forceinline__ void tile_contour_count(int label, bool inb, int p, int W, unsigned* s_last, unsigned* s_ccnt) {
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 31) s_last[warp] = (unsigned)label;
-  __syncthreads();
-  int left = __shfl_up_sync(0xffffffffu, label, 1);
-  if (lane == 0 && warp > 0) left = (int)s_last[warp - 1];
-  const bool c = inb && threadIdx.x > 0 && ((p % W) == 0 || label != left);
-  const unsigned b = __ballot_sync(0xffffffffu, c);
-  if (lane == 0 && b) atomicAdd(s_ccnt, (unsigned)__popc(b));
-}
-
-__device__ __forceinline__ void flush_tile_stats(int K, int f, int tile, int T, const unsigned* s_cnt,
-                                                 const unsigned long long* s_sum, const unsigned* s_flag,
-                                                 const unsigned* s_ccnt, const Book& bk) {
-  for (int l = threadIdx.x; l < K; l += blockDim.x) {
-    const unsigned c = s_cnt[l];
-    bk.tile_hist[((size_t)f * T + tile) * K + l] = (uint16_t)c;
-    if (c) {
-      atomicAdd(&bk.label_cnt[(size_t)f * K + l], c);
-      if (l >= 2) atomicAdd(&bk.label_sum[(size_t)f * K + l], s_sum[l]);
-    }
-  }
-  if (threadIdx.x == 0) {
-    bk.tile_ccnt[(size_t)f * T + tile] = (uint16_t)*s_ccnt;
-    if (*s_flag) atomicOr(&bk.flags[f], *s_flag);
-  }
-}
-
 __global__ void __launch_bounds__(kTile, 2)
 assign_labels_kernel(const float* __restrict__ range, const float* __restrict__ lut, const float* __restrict__ ground,
                      const float* __restrict__ centers, int HW, int W, int m, int T, uint8_t* __restrict__ labels,

@@ -52,7 +52,9 @@ point_model_kernel(const float* __restrict__ range, const uint8_t* __restrict__ 
   for (int q = 0; q < l; ++q) base += s_cnt[q];
 
   float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (l == 0) {
+  if (model == nullptr) {
+    // offsets only (decode path)
+  } else if (l == 0) {
     row = make_float4(ground[f * 4], ground[f * 4 + 1], ground[f * 4 + 2], ground[f * 4 + 3]);
   } else if (l >= 2) {
     const unsigned n = s_cnt[l];
@@ -71,7 +73,7 @@ point_model_kernel(const float* __restrict__ range, const uint8_t* __restrict__ 
       row.w = (float)(S / (double)n);
     }
   }
-  reinterpret_cast<float4*>(model)[(size_t)f * K + l] = row;
+  if (model != nullptr) reinterpret_cast<float4*>(model)[(size_t)f * K + l] = row;
 
   unsigned run = base;
   for (int t = 0; t < T; ++t) {
@@ -87,7 +89,8 @@ using namespace rpcc;
 
 extern "C" int rpcc_point_model_batch(const float* range, const uint8_t* labels, const float* ground, void* book,
                                       int B, int H, int W, int K, float* model, rpcc_frame_result* results, void* stream) {
-  RPCC_REQUIRE(range && labels && ground && book && model && results, "null pointer");
+  RPCC_REQUIRE(labels && book && results, "null pointer");
+  RPCC_REQUIRE(model == nullptr || (range && ground), "range and ground are needed to build models");
   RPCC_REQUIRE(K >= 2 && K <= 254, "K must be in [2, 254]");
   if (B == 0) return RPCC_OK;
   const int HW = H * W, T = (HW + RPCC_TILE - 1) / RPCC_TILE;

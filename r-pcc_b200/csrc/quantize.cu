@@ -25,11 +25,13 @@ __device__ __forceinline__ float predict_range(const float4 m, const float* __re
   return -m.w / (m.x * lut3[0] + m.y * lut3[1] + m.z * lut3[2]);
 }
 
+template <typename SymT>
 __global__ void __launch_bounds__(kQThreads, 1)
 quantize_pack_kernel(const float* __restrict__ range, const uint8_t* __restrict__ labels, const float* __restrict__ model,
                      const float* __restrict__ lut, Book bk, const float* __restrict__ step_per_label, float step,
-                     int HW, int W, int K, int T, int16_t* __restrict__ symbols, size_t sym_stride,
-                     uint8_t* __restrict__ contour_bits, int cbytes, uint16_t* __restrict__ seq, size_t seq_stride) {
+                     int HW, int W, int K, int T, SymT* __restrict__ symbols, size_t sym_stride,
+                     uint8_t* __restrict__ contour_bits, int cbytes, uint16_t* __restrict__ seq, size_t seq_stride,
+                     const unsigned long long* __restrict__ sym_base, const unsigned long long* __restrict__ seq_base) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* s_model = reinterpret_cast<float4*>(smem_raw);            // [K]
   float* s_step = reinterpret_cast<float*>(s_model + K);            // [K]
@@ -98,7 +100,7 @@ quantize_pack_kernel(const float* __restrict__ range, const uint8_t* __restrict_
 
   if (inb && label != 1) {
     const unsigned pos = s_tb[label] + s_wcnt[warp * K + label] + rank_in_warp;
-    symbols[(size_t)f * sym_stride + pos] = (int16_t)q;
+    symbols[(sym_base ? (size_t)sym_base[f] : (size_t)f * sym_stride) + pos] = (SymT)q;  // int16: wraps like astype(np.int16)
   }
   // idx_sequence position: contour bits before this pixel
   {
@@ -112,19 +114,63 @@ quantize_pack_kernel(const float* __restrict__ range, const uint8_t* __restrict_
     const unsigned before_warp = __shfl_sync(0xffffffffu, incl - wc, warp);
     if (cbit) {
       const unsigned pos = bk.tile_coff[(size_t)f * T + tile] + before_warp + __popc(cb & lanemask_lt());
-      seq[(size_t)f * seq_stride + pos] = (uint16_t)label;
+      seq[(seq_base ? (size_t)seq_base[f] : (size_t)f * seq_stride) + pos] = (uint16_t)label;
     }
   }
+}
+
+// exclusive scan of the per-frame symbol / sequence counts (one CTA; B <= 65535)
+__global__ void __launch_bounds__(1024)
+frame_offsets_kernel(const rpcc_frame_result* __restrict__ results, int B, unsigned long long* __restrict__ sym_base,
+                     unsigned long long* __restrict__ seq_base) {
+  __shared__ unsigned long long s_a[32], s_b[32];
+  __shared__ unsigned long long s_run[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { s_run[0] = 0; s_run[1] = 0; }
+  __syncthreads();
+  for (int b0 = 0; b0 < B; b0 += 1024) {
+    const int b = b0 + tid;
+    const unsigned long long a = b < B ? results[b].sym_count : 0ull;
+    const unsigned long long c = b < B ? results[b].seq_count : 0ull;
+    unsigned long long ia = a, ic = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long va = __shfl_up_sync(0xffffffffu, ia, o), vc = __shfl_up_sync(0xffffffffu, ic, o);
+      if (lane >= o) { ia += va; ic += vc; }
+    }
+    if (lane == 31) { s_a[warp] = ia; s_b[warp] = ic; }
+    __syncthreads();
+    unsigned long long wa = 0, wc = 0;
+    for (int q = 0; q < warp; ++q) { wa += s_a[q]; wc += s_b[q]; }
+    if (b < B) { sym_base[b] = s_run[0] + wa + ia - a; seq_base[b] = s_run[1] + wc + ic - c; }
+    __syncthreads();
+    if (tid == 1023) { s_run[0] += wa + ia; s_run[1] += wc + ic; }
+    __syncthreads();
+  }
+  if (tid == 0) { sym_base[B] = s_run[0]; seq_base[B] = s_run[1]; }
 }
 
 }  // namespace rpcc
 
 using namespace rpcc;
 
-extern "C" int rpcc_quantize_pack_batch(const float* range, const uint8_t* labels, const float* model, const float* lut,
-                                        void* book, const float* step_per_label, float step, int B, int H, int W, int K,
-                                        int16_t* symbols, size_t sym_stride, uint8_t* contour_bits, uint16_t* seq,
-                                        size_t seq_stride, void* stream) {
+extern "C" int rpcc_frame_offsets_batch(const rpcc_frame_result* results, int B, uint64_t* sym_base, uint64_t* seq_base,
+                                        void* stream) {
+  RPCC_REQUIRE(results && sym_base && seq_base, "null pointer");
+  frame_offsets_kernel<<<1, 1024, 0, as_stream(stream)>>>(results, B, reinterpret_cast<unsigned long long*>(sym_base),
+                                                          reinterpret_cast<unsigned long long*>(seq_base));
+  RPCC_LAUNCH_CHECK("frame_offsets_kernel");
+  return RPCC_OK;
+}
+
+namespace rpcc {
+// SymT = int16_t: the bitstream type (utils/compress_utils.py:142); int32_t: what
+// uniform_quantize / nonuniform_quantize themselves return (cpp_modules.cpp:322,408).
+template <typename SymT>
+int quantize_pack_launch(const float* range, const uint8_t* labels, const float* model, const float* lut, void* book,
+                         const float* step_per_label, float step, int B, int H, int W, int K, SymT* symbols,
+                         size_t sym_stride, uint8_t* contour_bits, uint16_t* seq, size_t seq_stride,
+                         const uint64_t* sym_base, const uint64_t* seq_base, void* stream) {
   RPCC_REQUIRE(range && labels && model && lut && book && symbols && contour_bits && seq, "null pointer");
   RPCC_REQUIRE(K >= 2 && K <= 254, "K must be in [2, 254]");
   RPCC_REQUIRE(B <= 65535, "at most 65535 frames per launch");
@@ -133,9 +179,23 @@ extern "C" int rpcc_quantize_pack_batch(const float* range, const uint8_t* label
   const Book bk = make_book(book, B, T, K);
   const size_t smem = (sizeof(float4) + sizeof(float) + sizeof(unsigned)) * K + sizeof(unsigned) * 64 +
                       sizeof(uint16_t) * 32 * (size_t)K + 16;
-  quantize_pack_kernel<<<dim3(T, B), kQThreads, smem, as_stream(stream)>>>(
+  quantize_pack_kernel<SymT><<<dim3(T, B), kQThreads, smem, as_stream(stream)>>>(
       range, labels, model, lut, bk, step_per_label, step, HW, W, K, T, symbols, sym_stride, contour_bits,
-      (HW + 7) / 8, seq, seq_stride);
+      (HW + 7) / 8, seq, seq_stride, reinterpret_cast<const unsigned long long*>(sym_base),
+      reinterpret_cast<const unsigned long long*>(seq_base));
   RPCC_LAUNCH_CHECK("quantize_pack_kernel");
   return RPCC_OK;
+}
+template int quantize_pack_launch<int32_t>(const float*, const uint8_t*, const float*, const float*, void*, const float*, float,
+                                           int, int, int, int, int32_t*, size_t, uint8_t*, uint16_t*, size_t, const uint64_t*,
+                                           const uint64_t*, void*);
+}  // namespace rpcc
+
+extern "C" int rpcc_quantize_pack_batch(const float* range, const uint8_t* labels, const float* model, const float* lut,
+                                        void* book, const float* step_per_label, float step, int B, int H, int W, int K,
+                                        int16_t* symbols, size_t sym_stride, uint8_t* contour_bits, uint16_t* seq,
+                                        size_t seq_stride, const uint64_t* sym_base, const uint64_t* seq_base,
+                                        void* stream) {
+  return quantize_pack_launch<int16_t>(range, labels, model, lut, book, step_per_label, step, B, H, W, K, symbols, sym_stride,
+                                       contour_bits, seq, seq_stride, sym_base, seq_base, stream);
 }

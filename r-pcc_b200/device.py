@@ -107,5 +107,5 @@ def quantize_pack_batch(rng, labels, model, lut, book, step, step_per_label=None
     seq = torch.empty((B, HW), dtype=torch.int16, device=rng.device)  # uint16 payload
     check(_lib.lib().rpcc_quantize_pack_batch(ptr(rng), ptr(labels), ptr(model), ptr(lut), ptr(book),
                                               ptr(step_per_label), C.c_float(step), B, H, W, K, ptr(symbols),
-                                              C.c_size_t(HW), ptr(contour), ptr(seq), C.c_size_t(HW), _stream()))
+                                              C.c_size_t(HW), ptr(contour), ptr(seq), C.c_size_t(HW), None, None, _stream()))
     return symbols, contour, seq

@@ -1,0 +1,142 @@
+"""Pins the CPU oracle (oracle/liborc.so) BEFORE it is trusted as a checker:
+  * against tests/golden/example_golden.npz, produced by the reference's own Python + C++ on
+    assets/example_data/example.bin (tests/golden/make_golden.py);
+  * against the reference's compiled C++ (oracle/_ref) on synthetic frames of every lidar, when present;
+  * against the only known-answer vector the reference holds (ContourExtractor docstring);
+  * its restated glibc atan2f against the libm of the machine the test runs on."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import ref
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "example_golden.npz")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+@pytest.mark.parametrize("tag,nonuniform", [("u", False), ("n", True)])
+def test_oracle_matches_reference_golden(example_points, gold, tag, nonuniform):
+    out = oracle.compress_frame(example_points, "Velodyne64E", gold["ground"], accuracy=0.02, nonuniform=nonuniform)
+    g = lambda k: gold[tag + "_" + k]  # noqa: E731
+    assert sha(out["range_image"]) == str(g("range_sha"))
+    assert int((out["range_image"] != 0).sum()) == int(g("valid")) == 94053
+    assert np.array_equal(out["seg_idx"].astype(np.uint8), g("seg_u8"))
+    assert np.array_equal(out["center_idx"], g("center_idx"))
+    assert out["model_param"].tobytes() == g("model_param").tobytes()
+    assert sha(out["pred"]) == str(g("pred_sha"))
+    assert np.array_equal(out["symbols"].astype(np.int16), g("symbols"))
+    sec = out["sections"]
+    assert sec["contour_map"] == g("contour_bits").tobytes()
+    assert sec["idx_sequence"] == g("idx_sequence").tobytes()
+    if nonuniform:
+        assert np.array_equal(out["key_point_map"].astype(np.uint8), g("key_points_u8"))
+        assert np.array_equal(out["salience_level"].astype(np.uint8), g("salience"))
+    # the .rpcc file, byte for byte (bz2 level 9 is deterministic)
+    assert oracle.write_rpcc(sec, "bzip2") == g("rpcc").tobytes()
+    rec, xyz, seg = oracle.decompress_sections(sec, "Velodyne64E", 0.02)
+    assert sha(rec[..., None]) == str(g("rec_sha"))
+    assert sha(xyz) == str(g("xyz_sha"))
+    bound = 0.02 if not nonuniform else 0.02 + 0.03
+    assert float(np.abs(rec - out["range_image"]).max()) <= bound + 1e-5
+
+
+def test_contour_known_answer(gold):
+    contour, seq = oracle.extract_contour(gold["kat_idx_map"])
+    assert np.array_equal(contour, gold["kat_contour"])
+    assert np.array_equal(seq, gold["kat_seq"])
+    assert np.array_equal(oracle.recover_map(contour, seq), gold["kat_idx_map"])
+
+
+@pytest.mark.skipif(not ref.have_cpp(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("lidar", ["Velodyne64E", "Velodyne32E", "VelodyneVLP16"])
+def test_oracle_matches_compiled_reference(lidar):
+    from rpcc_b200 import synthetic
+    d, s, q, c, f = (ref.cpp(n) for n in ("dataset_utils_cpp", "segment_utils_cpp", "quantization_utils_cpp",
+                                          "contour_utils_cpp", "feature_extractor_cpp"))
+    H, W, hf, vmax, vmin = oracle.lidar_params(lidar)
+    lut = oracle.transform_map(H, W, hf, vmax, vmin)
+    for seed in (11, 12):
+        pts, ground = synthetic.frame(seed, lidar)
+        ri = oracle.project(pts, H, W, hf, vmax, vmin)
+        assert np.array_equal(ri.view(np.uint32), d.point_cloud_to_range_image_even(
+            np.ascontiguousarray(pts[:, :3]), H, W, hf, vmax, vmin).view(np.uint32))
+        assert np.array_equal(ri, oracle.project(pts, H, W, hf, vmax, vmin, restated_atan2=True))
+        seg, _, _ = oracle.segment(ri, lut, ground, 100)
+        pm = oracle.point_modeling(ri, seg)
+        assert pm.tobytes() == s.point_modeling(ri[..., None], seg).tobytes()
+        mp = oracle.model_param_point(ri, seg, ground)
+        pred = oracle.intra_predict(seg, mp, lut)
+        assert pred.tobytes() == s.intra_predict(seg, mp, lut).tobytes()
+        res = ri - pred
+        assert np.array_equal(oracle.uniform_quantize(seg, res, 0.04), q.uniform_quantize(seg, res[..., None], 0.04))
+        _, kp = oracle.extract_features(ri, seg)
+        kp_r = _ref_keypoints_zeroed_heap(ri, seg)
+        assert np.array_equal(kp, kp_r)
+        acc = np.array([0.04] * 4) + np.array([0, 0.02, 0.04, 0.06])
+        sy, sl = oracle.nonuniform_quantize(seg, res, kp, (30, 10, 3, 0), acc, 2)
+        sy_r, sl_r = q.nonuniform_quantize(seg, res[..., None], kp, np.array((30, 10, 3, 0)), acc, 2)
+        assert np.array_equal(sy, sy_r) and np.array_equal(sl, sl_r)
+        ct, sq = oracle.extract_contour(seg)
+        ct_r, sq_r = c.extract_contour(seg)
+        assert np.array_equal(ct, ct_r) and np.array_equal(sq, sq_r)
+        assert np.array_equal(oracle.recover_map(ct, sq), c.recover_map(ct_r, sq_r))
+
+
+def _ref_keypoints_zeroed_heap(ri, seg):
+    """The reference's extract_features_with_segment never zero-fills its output, so it is
+    run in a child process whose malloc zero-fills (glibc MALLOC_PERTURB_=255): the deterministic reading."""
+    import subprocess
+    import sys
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as d:
+        np.savez(os.path.join(d, "in.npz"), ri=ri, seg=seg)
+        code = ("import sys, numpy as np; sys.path.insert(0, %r); from oracle import ref; "
+                "z = np.load(%r); f = ref.cpp('feature_extractor_cpp'); "
+                "_, kp = f.extract_features_with_segment(z['ri'], z['seg'], 3, 8, 4, 8, 6); np.save(%r, kp)"
+                % (root, os.path.join(d, "in.npz"), os.path.join(d, "kp.npy")))
+        subprocess.check_call([sys.executable, "-c", code], env=dict(os.environ, MALLOC_PERTURB_="255"))
+        return np.load(os.path.join(d, "kp.npy"))
+
+
+def test_restated_atan2f_matches_libm():
+    g = np.random.default_rng(5)
+    n = 2_000_000
+    x = (g.standard_normal(n) * 40).astype(np.float32)
+    y = (g.standard_normal(n) * 40).astype(np.float32)
+    a, b = oracle.atan2f_pair(y, x)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    # vertical-angle style inputs (z, planar distance), axis-aligned and signed-zero cases
+    z = (g.standard_normal(n) * 3).astype(np.float32)
+    d = np.abs(x) + np.float32(0.5)
+    a, b = oracle.atan2f_pair(z, d)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    sp_y = np.array([0.0, -0.0, 0.0, -0.0, 1.0, -1.0, 0.0, 5.0, -5.0, 1e-30, 3.0], np.float32)
+    sp_x = np.array([0.0, 0.0, -0.0, -0.0, 0.0, 0.0, 1.0, 1.0, 1.0, 1.0, -1e-30], np.float32)
+    a, b = oracle.atan2f_pair(sp_y, sp_x)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_fps_tie_rule_matches_tree_order():
+    """All-identical points: the reference tree picks min bit-reversed (k mod 1024), then min k."""
+    pts = np.zeros((3000, 3), np.float32)
+    idx = oracle.fps(pts, 4)
+    assert idx.tolist() == [0, 0, 0, 0]
+    pts[5:] = 1.0  # points 0..4 at the origin, the rest identical and tied: residue class 0 wins
+    idx = oracle.fps(pts, 3)   # (bit-reversed thread id 0), and inside it the lowest k that is not an origin point
+    assert idx[1] == 1024
+    pts[1024] = 0.0            # take that one out: class 0 still wins through k = 2048
+    assert oracle.fps(pts, 3)[1] == 2048
+    pts[2048] = 0.0            # class 0 exhausted: next is thread 512 (bit-reversed id 1)
+    assert oracle.fps(pts, 3)[1] == 512
