@@ -25,26 +25,47 @@ namespace rpcc {
 
 constexpr int kTile = RPCC_TILE;  // 1024 threads, one pixel each
 
+// Centres are kept sorted by their distance to the sensor; a pixel at range r only has to look at the
+// centres whose norm lies within its current best distance of r (| |p| - |c| | <= |p - c|), walking
+// outwards from r and stopping as soon as the nearer side of the window is out of reach.  The skip
+// test carries a slack that covers every float rounding involved (|p| vs r, the computed norms, the
+// reference's own distance arithmetic), so a skipped centre can neither beat nor tie the current
+// best; the evaluated ones use the reference arithmetic verbatim, with torch.max's first-index rule.
 __global__ void __launch_bounds__(kTile, 2)
 assign_labels_kernel(const float* __restrict__ range, const float* __restrict__ lut, const float* __restrict__ ground,
                      const float* __restrict__ centers, int HW, int W, int m, int T, uint8_t* __restrict__ labels,
                      Book bk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int K = m + 2;
-  float4* s_c = reinterpret_cast<float4*>(smem_raw);                               // [m] centres
+  float4* s_c = reinterpret_cast<float4*>(smem_raw);                               // [m] centres sorted by norm: x,y,z,norm
   unsigned long long* s_sum = reinterpret_cast<unsigned long long*>(s_c + m);     // [K]
   unsigned* s_cnt = reinterpret_cast<unsigned*>(s_sum + K);                       // [K]
   unsigned* s_flag = s_cnt + K;
   unsigned* s_ccnt = s_flag + 1;
   unsigned* s_last = s_ccnt + 1;                                                  // [32]
+  float* s_norm = reinterpret_cast<float*>(s_last + 32);                          // [m] unsorted norms (scratch)
+  unsigned char* s_id = reinterpret_cast<unsigned char*>(s_norm + m);             // [m] original index of sorted slot
 
   const int f = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
-  for (int c = tid; c < m; c += kTile) {
-    const float* cp = centers + ((size_t)f * m + c) * 3;
-    s_c[c] = make_float4(cp[0], cp[1], cp[2], 0.f);
+  float cx = 0.f, cy = 0.f, cz = 0.f, cn = 0.f;
+  if (tid < m) {
+    const float* cp = centers + ((size_t)f * m + tid) * 3;
+    cx = cp[0]; cy = cp[1]; cz = cp[2];
+    cn = sqrtf(cx * cx + cy * cy + cz * cz);
+    s_norm[tid] = cn;
   }
   for (int l = tid; l < K; l += kTile) { s_cnt[l] = 0; s_sum[l] = 0; }
   if (tid == 0) { *s_flag = 0; *s_ccnt = 0; }
+  __syncthreads();
+  if (tid < m) {
+    int rank = 0;  // counting sort position: (norm, index) ascending
+    for (int q = 0; q < m; ++q) {
+      const float o = s_norm[q];
+      rank += (o < cn || (o == cn && q < tid)) ? 1 : 0;
+    }
+    s_c[rank] = make_float4(cx, cy, cz, cn);
+    s_id[rank] = (unsigned char)tid;
+  }
   __syncthreads();
 
   const int p = tile * kTile + tid;
@@ -60,17 +81,32 @@ assign_labels_kernel(const float* __restrict__ range, const float* __restrict__ 
       const float rplane = (-g3) / torch_sum3(g0 * t0, g1 * t1, g2 * t2);
       float best = fabsf(r - rplane);
       int bi = 0;
-      float thresh = __int_as_float(0x7f800000);  // +inf: smallest squared distance examined so far
-#pragma unroll 4
-      for (int c = 0; c < m; ++c) {
-        const float4 cc = s_c[c];
+      // lower bound: first sorted slot whose norm is >= r
+      int lo = 0, n = m;
+      while (n > 0) {
+        const int half = n >> 1;
+        const bool right = s_c[lo + half].w < r;
+        lo = right ? lo + half + 1 : lo;
+        n = right ? n - half - 1 : half;
+      }
+      int hi = lo;      // next slot above r
+      lo = lo - 1;      // next slot below r
+      while (true) {
+        const float dlo = lo >= 0 ? r - s_c[lo >= 0 ? lo : 0].w : __int_as_float(0x7f800000);
+        const float dhi = hi < m ? s_c[hi < m ? hi : 0].w - r : __int_as_float(0x7f800000);
+        const bool take_lo = dlo <= dhi;
+        const float dn = take_lo ? dlo : dhi;
+        const int slot = take_lo ? lo : hi;
+        if (slot < 0 || slot >= m) break;                      // both sides exhausted
+        const float4 cc = s_c[slot];
+        // | |p| - |c| | with every rounding on the safe side; NaN best (degenerate ground plane) never skips
+        if ((dn - 2e-6f * (r + cc.w)) * 0.99999f > best) break;
+        lo = take_lo ? lo - 1 : lo;
+        hi = take_lo ? hi : hi + 1;
         const float dx = x - cc.x, dy = y - cc.y, dz = z - cc.z;
-        const float ss = torch_sum3(dx * dx, dy * dy, dz * dz);
-        if (ss < thresh) {
-          thresh = ss;
-          const float v = sqrtf(ss);
-          if (v < best) { best = v; bi = c + 1; }
-        }
+        const float v = sqrtf(torch_sum3(dx * dx, dy * dy, dz * dz));
+        const int ci = (int)s_id[slot] + 1;
+        if (v < best || (v == best && ci < bi)) { best = v; bi = ci; }
       }
       label = bi > 0 ? bi + 1 : 0;
     }
@@ -137,7 +173,8 @@ extern "C" int rpcc_assign_labels_batch(const float* range, const float* lut, co
   const Book bk = make_book(book, B, T, K);
   int rc = zero_book(bk, B, K, st);
   if (rc != RPCC_OK) return rc;
-  const size_t smem = sizeof(float4) * m + (sizeof(unsigned long long) + sizeof(unsigned)) * K + sizeof(unsigned) * 34;
+  const size_t smem = sizeof(float4) * m + (sizeof(unsigned long long) + sizeof(unsigned)) * K + sizeof(unsigned) * 34 +
+                      sizeof(float) * m + m + 16;
   assign_labels_kernel<<<dim3(T, B), kTile, smem, st>>>(range, lut, ground, centers, HW, W, m, T, labels, bk);
   RPCC_LAUNCH_CHECK("assign_labels_kernel");
   return RPCC_OK;

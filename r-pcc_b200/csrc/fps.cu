@@ -99,19 +99,30 @@ fps_generic_kernel(const float* __restrict__ points, int n, int m, int log2bs, f
 // fused mask + FPS, one 8-CTA cluster per frame
 // ------------------------------------------------------------------------------------------------
 constexpr int kCl = 8;            // CTAs per cluster
-constexpr int kFpsThreads = 1024; // = the reference's block size, so thread id == residue class
-constexpr int kRegSlots = 4;
+constexpr int kFpsThreads = 1024; // = the reference's block size, so thread id == residue class k mod 1024
+constexpr int kRegSlots = 6;      // candidate points per thread kept in registers; the rest in shared memory
 
-struct __align__(16) FpsRecord { unsigned long long key; float x, y, z; int pad; };
+// one candidate: squared distance (as ordered bits), tie key, coordinates
+struct __align__(16) FpsRecord { unsigned d, tk; float x, y; float z; int pad0, pad1, pad2; };
 
 // torch float32 semantics of utils/segment_utils.py:137-139 for one pixel:
-// |sum(pc*g)+g3| / norm(g) > thr ? pc : 0   (size-3 reductions associate as (t0+t2)+t1, see assign.cu)
+// |sum(pc*g)+g3| / norm(g) > thr ? pc : 0   (size-3 reductions associate as torch_sum3)
 __device__ __forceinline__ void masked_point(float r, const float* __restrict__ lut3, float g0, float g1, float g2,
                                              float g3, float gnorm, float thr, float& x, float& y, float& z) {
   x = r * lut3[0]; y = r * lut3[1]; z = r * lut3[2];
   const float s = torch_sum3(x * g0, y * g1, z * g2);
   const float dif = fabsf(s + g3) / gnorm;
   if (!(dif > thr)) { x = 0.f; y = 0.f; z = 0.f; }
+}
+
+// winner among the lanes of a warp: max d (bit pattern of a non-negative float), then min tie key.
+// Returns the owning lane (every lane gets the same answer); lanes without a candidate pass d = 0, tk = ~0.
+__device__ __forceinline__ int warp_winner(unsigned d, unsigned tk, unsigned& dmax, unsigned& tkmin) {
+  dmax = __reduce_max_sync(0xffffffffu, d);
+  const unsigned t = d == dmax ? tk : 0xFFFFFFFFu;
+  tkmin = __reduce_min_sync(0xffffffffu, t);
+  const unsigned own = __ballot_sync(0xffffffffu, t == tkmin);
+  return __ffs(own) - 1;
 }
 
 template <int SLOTS>
@@ -123,17 +134,17 @@ segment_fps_kernel(const float* __restrict__ range, const float* __restrict__ lu
   const int ncluster = gridDim.x / kCl;
   const int cid = blockIdx.x / kCl;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int SM = SLOTS - kRegSlots;  // shared-memory slots
+  constexpr int RS = SLOTS < kRegSlots ? SLOTS : kRegSlots;  // register slots
+  constexpr int SM = SLOTS - RS;                             // shared-memory slots
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* sx = reinterpret_cast<float*>(smem_raw);
+  FpsRecord* s_part = reinterpret_cast<FpsRecord*>(smem_raw);                 // [2][32] per-warp winners
+  FpsRecord* s_rec = s_part + 64;                                             // [2][kCl] per-CTA winners (written remotely)
+  float* sx = reinterpret_cast<float*>(s_rec + 2 * kCl);                      // [SM][1024]
   float* sy = sx + SM * kFpsThreads;
   float* sz = sy + SM * kFpsThreads;
-  unsigned char* sj = reinterpret_cast<unsigned char*>(sz + SM * kFpsThreads);   // [SLOTS][1024] row of each slot
-  unsigned long long* s_part = reinterpret_cast<unsigned long long*>(sj + SLOTS * kFpsThreads);  // [2][32]
-  FpsRecord* s_rec = reinterpret_cast<FpsRecord*>(s_part + 64);                   // [2][kCl]
+  unsigned char* sj = reinterpret_cast<unsigned char*>(sz + SM * kFpsThreads);  // [SLOTS][1024] row (k >> 10) of each slot
 
-  const int J = (HW + kFpsThreads - 1) / kFpsThreads;
   const unsigned tie_hi = __brev((unsigned)tid) & 0xFFC00000u;  // bitrev10(tid) in the top 10 bits
   unsigned par = 0;
 
@@ -142,35 +153,37 @@ segment_fps_kernel(const float* __restrict__ range, const float* __restrict__ lu
     const float g0 = ground[f * 4], g1 = ground[f * 4 + 1], g2 = ground[f * 4 + 2], g3 = ground[f * 4 + 3];
     const float gnorm = sqrtf(torch_sum3(g0 * g0, g1 * g1, g2 * g2));
 
-    // ---- gather this thread's share of residue class `tid`: items are the non-origin points plus
-    //      the first origin pixel, dealt round-robin (by rank inside the class) to the 8 CTAs.
-    float rx[kRegSlots], ry[kRegSlots], rz[kRegSlots];
+    // ---- gather: CTA `rank` owns the rows j = rank, rank+8, ... of the reference's (row j, thread tid)
+    //      layout k = j*1024 + tid.  Kept per thread, in increasing k: every non-origin point and the
+    //      first origin point (ground / empty pixels are all the same point; the first one carries the
+    //      best tie key of its residue class inside this CTA).
+    float rx[RS], ry[RS], rz[RS];
 #pragma unroll
-    for (int s = 0; s < kRegSlots; ++s) { rx[s] = 0.f; ry[s] = 0.f; rz[s] = 0.f; }
-    int mine = 0, seen = 0;
+    for (int s = 0; s < RS; ++s) { rx[s] = 0.f; ry[s] = 0.f; rz[s] = 0.f; }
+    int mine = 0;
     bool origin_seen = false;
-#pragma unroll 5
-    for (int j = 0; j < J; ++j) {
+#pragma unroll 4
+    for (int jj = 0; jj < SLOTS; ++jj) {
+      const int j = jj * kCl + rank;
       const int k = j * kFpsThreads + tid;
-      if (k >= HW) break;
-      float x, y, z;
-      masked_point(rg[k], lut + (size_t)k * 3, g0, g1, g2, g3, gnorm, thr, x, y, z);
-      const bool origin = (x == 0.f) && (y == 0.f) && (z == 0.f);
-      if (origin && origin_seen) continue;
-      origin_seen = origin_seen || origin;
-      const int r = seen++;
-      if ((r & (kCl - 1)) != rank) continue;
-      if (mine < kRegSlots) {
+      if (k < HW) {
+        float x, y, z;
+        masked_point(rg[k], lut + (size_t)k * 3, g0, g1, g2, g3, gnorm, thr, x, y, z);
+        const bool origin = (x == 0.f) && (y == 0.f) && (z == 0.f);
+        if (!(origin && origin_seen)) {
+          origin_seen = origin_seen || origin;
+          if (mine < RS) {
 #pragma unroll
-        for (int s = 0; s < kRegSlots; ++s) if (mine == s) { rx[s] = x; ry[s] = y; rz[s] = z; }
-      } else if (mine < SLOTS) {
-        const int o = (mine - kRegSlots) * kFpsThreads + tid;
-        sx[o] = x; sy[o] = y; sz[o] = z;
+            for (int s = 0; s < RS; ++s) if (mine == s) { rx[s] = x; ry[s] = y; rz[s] = z; }
+          } else {
+            const int o = (mine - RS) * kFpsThreads + tid;
+            sx[o] = x; sy[o] = y; sz[o] = z;
+          }
+          sj[mine * kFpsThreads + tid] = (unsigned char)j;
+          ++mine;
+        }
       }
-      if (mine < SLOTS) sj[mine * kFpsThreads + tid] = (unsigned char)j;
-      ++mine;
     }
-    mine = mine < SLOTS ? mine : SLOTS;
     int wmax = mine;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
@@ -196,66 +209,79 @@ segment_fps_kernel(const float* __restrict__ range, const float* __restrict__ lu
         if (s >= wmax) break;  // warp-uniform
         if (s < mine) {
           float px, py, pz;
-          if (s < kRegSlots) { px = rx[s < kRegSlots ? s : 0]; py = ry[s < kRegSlots ? s : 0]; pz = rz[s < kRegSlots ? s : 0]; }
-          else { const int o = (s - kRegSlots) * kFpsThreads + tid; px = sx[o]; py = sy[o]; pz = sz[o]; }
+          if (s < RS) { px = rx[s < RS ? s : 0]; py = ry[s < RS ? s : 0]; pz = rz[s < RS ? s : 0]; }
+          else { const int o = (s - RS) * kFpsThreads + tid; px = sx[o]; py = sy[o]; pz = sz[o]; }
           const float d2 = fminf(fps_dist(px, py, pz, x1, y1, z1), temp[s]);
           temp[s] = d2;
           if (d2 > best) { best = d2; bs = s; }
         }
       }
-      unsigned long long mykey = 0;
-      if (mine > 0) mykey = make_key(best, tie_hi | (unsigned)sj[bs * kFpsThreads + tid]);
-      unsigned long long key = warp_key_max(mykey);
-      if (lane == 0) s_part[par * 32 + warp] = key;
-      __syncthreads();
-      key = warp_key_max(s_part[par * 32 + lane]);
-      // the owner of the CTA winner publishes it to every CTA of the cluster
-      if ((key != 0 && mykey == key) || (key == 0 && tid == 0)) {
-        FpsRecord rec;
-        rec.key = key; rec.pad = 0;
-        if (key != 0) {
-          if (bs < kRegSlots) {
-            rec.x = rx[0]; rec.y = ry[0]; rec.z = rz[0];
-#pragma unroll
-            for (int s = 1; s < kRegSlots; ++s) if (bs == s) { rec.x = rx[s]; rec.y = ry[s]; rec.z = rz[s]; }
-          } else {
-            const int o = (bs - kRegSlots) * kFpsThreads + tid;
-            rec.x = sx[o]; rec.y = sy[o]; rec.z = sz[o];
-          }
-        } else {
+      // ---- warp winner -> shared
+      {
+        const unsigned d = mine > 0 ? __float_as_uint(best) : 0u;
+        // the tie key (one shared-memory read) is only needed by lanes that hold the warp maximum
+        const unsigned dmax = __reduce_max_sync(0xffffffffu, d);
+        const unsigned tk = (mine > 0 && d == dmax) ? (tie_hi | (unsigned)sj[bs * kFpsThreads + tid]) : 0xFFFFFFFFu;
+        const unsigned tkmin = __reduce_min_sync(0xffffffffu, tk);
+        const int own = __ffs(__ballot_sync(0xffffffffu, tk == tkmin)) - 1;
+        if (lane == own) {
+          FpsRecord rec;
+          rec.d = dmax; rec.tk = tkmin; rec.pad0 = 0; rec.pad1 = 0; rec.pad2 = 0;
           rec.x = 0.f; rec.y = 0.f; rec.z = 0.f;
-        }
+          if (tkmin != 0xFFFFFFFFu) {
+            if (bs < RS) {
 #pragma unroll
-        for (int r = 0; r < kCl; ++r) {
-          FpsRecord* dst = cluster.map_shared_rank(s_rec, r) + par * kCl + rank;
-          *dst = rec;
+              for (int s = 0; s < RS; ++s) if (bs == s) { rec.x = rx[s]; rec.y = ry[s]; rec.z = rz[s]; }
+            } else {
+              const int o = (bs - RS) * kFpsThreads + tid;
+              rec.x = sx[o]; rec.y = sy[o]; rec.z = sz[o];
+            }
+          }
+          s_part[par * 32 + warp] = rec;
+        }
+      }
+      __syncthreads();
+      // ---- CTA winner: warp 0 only, published to every CTA of the cluster through DSMEM
+      if (warp == 0) {
+        const FpsRecord mineRec = s_part[par * 32 + lane];
+        unsigned dmax, tkmin;
+        const int own = warp_winner(mineRec.d, mineRec.tk, dmax, tkmin);
+        if (lane == own) {
+#pragma unroll
+          for (int r = 0; r < kCl; ++r) {
+            FpsRecord* dst = cluster.map_shared_rank(s_rec, r) + par * kCl + rank;
+            *dst = mineRec;
+          }
         }
       }
       cluster.sync();
-      FpsRecord w = s_rec[par * kCl];
-#pragma unroll
-      for (int r = 1; r < kCl; ++r) {
-        const FpsRecord o = s_rec[par * kCl + r];
-        if (o.key > w.key) w = o;
-      }
-      x1 = w.x; y1 = w.y; z1 = w.z;
-      if (rank == 0 && tid == 0) {
-        const unsigned tiekey = 0xFFFFFFFFu - (unsigned)(w.key & 0xFFFFFFFFull);
-        const int k = (int)(((tiekey & 0x3FFFFFu) << 10) | (__brev(tiekey & 0xFFC00000u)));
-        center_idx[(size_t)f * m + j] = k;
-        float* c = centers + ((size_t)f * m + j) * 3;
-        c[0] = x1; c[1] = y1; c[2] = z1;
+      // ---- cluster winner: every warp reduces the 8 records on its own
+      {
+        FpsRecord w;
+        w.d = 0u; w.tk = 0xFFFFFFFFu; w.x = 0.f; w.y = 0.f; w.z = 0.f;
+        if (lane < kCl) w = s_rec[par * kCl + lane];
+        unsigned dmax, tkmin;
+        const int own = warp_winner(w.d, w.tk, dmax, tkmin);
+        x1 = __shfl_sync(0xffffffffu, w.x, own);
+        y1 = __shfl_sync(0xffffffffu, w.y, own);
+        z1 = __shfl_sync(0xffffffffu, w.z, own);
+        if (rank == 0 && tid == 0) {
+          const int k = (int)(((tkmin & 0x3FFFFFu) << 10) | (__brev(tkmin & 0xFFC00000u)));
+          center_idx[(size_t)f * m + j] = k;
+          float* c = centers + ((size_t)f * m + j) * 3;
+          c[0] = x1; c[1] = y1; c[2] = z1;
+        }
       }
     }
-    // slots are rewritten by the next frame's gather only after every thread of this CTA left the
-    // round loop; remote records use the other parity buffer first, so no extra cluster barrier.
+    // the next frame's gather rewrites the shared slots: every thread must have left the round loop
     __syncthreads();
   }
 }
 
 template <int SLOTS>
 static size_t fps_smem_bytes() {
-  return (size_t)(SLOTS - kRegSlots) * kFpsThreads * 12 + (size_t)SLOTS * kFpsThreads + 64 * 8 + 2 * kCl * sizeof(FpsRecord);
+  constexpr int RS = SLOTS < kRegSlots ? SLOTS : kRegSlots;
+  return (size_t)(SLOTS - RS) * kFpsThreads * 12 + (size_t)SLOTS * kFpsThreads + (64 + 2 * kCl) * sizeof(FpsRecord);
 }
 
 template <int SLOTS>

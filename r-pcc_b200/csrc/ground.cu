@@ -17,7 +17,7 @@
 
 namespace rpcc {
 
-constexpr int kGfThreads = 256;
+constexpr int kGfThreads = 1024;
 constexpr int kGfMaxPts = 5000;
 constexpr int kGfIters = 100;
 constexpr int kGfSample = 10;
@@ -59,7 +59,6 @@ ground_fit_kernel(const float* __restrict__ range, const float* __restrict__ lut
   float* py = px + kGfMaxPts;
   float* pz = py + kGfMaxPts;
   __shared__ int s_warp[kGfThreads / 32];
-  __shared__ int s_count;
   __shared__ double s_plane[kGfIters][4];
   __shared__ unsigned long long s_score[kGfIters];  // (inliers << 32) | ~quantised rmse  (max wins)
   __shared__ double s_sums[10];
@@ -69,49 +68,44 @@ ground_fit_kernel(const float* __restrict__ range, const float* __restrict__ lut
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* rg = range + (size_t)f * HW;
 
+  // Each warp owns a contiguous segment of the image, so the candidate order is the raster order
+  // and no block-wide synchronisation is needed inside the two passes.
+  constexpr int NW = kGfThreads / 32;
+  const int seg_len = (HW + NW - 1) / NW;
+  const int p_begin = warp * seg_len;
+  const int p_end = min(HW, p_begin + seg_len);
   // pass 1: count candidates (z < z_below; empty pixels have z = 0)
   int cnt = 0;
-  for (int p = tid; p < HW; p += kGfThreads) cnt += (rg[p] * lut[(size_t)p * 3 + 2] < z_below) ? 1 : 0;
+  for (int p = p_begin + lane; p < p_end; p += 32) cnt += (rg[p] * lut[(size_t)p * 3 + 2] < z_below) ? 1 : 0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   if (lane == 0) s_warp[warp] = cnt;
   __syncthreads();
-  if (tid == 0) {
-    int t = 0;
-    for (int q = 0; q < kGfThreads / 32; ++q) t += s_warp[q];
-    s_count = t;
-  }
-  __syncthreads();
-  int nc = s_count;
+  int nc = 0, base = 0;
+  for (int q = 0; q < NW; ++q) { const int c = s_warp[q]; if (q < warp) base += c; nc += c; }
   const bool use_all = nc < 800;  // segment_utils.py:105-106
-  if (use_all) nc = HW;
+  if (use_all) { nc = HW; base = p_begin; }
   const int ns = nc < kGfMaxPts ? nc : kGfMaxPts;
-  __syncthreads();
 
   // pass 2: keep an even stride of the candidates, in raster order
-  int base = 0;
-  for (int p0 = 0; p0 < HW; p0 += kGfThreads) {
-    const int p = p0 + tid;
+  for (int p0 = p_begin; p0 < p_end; p0 += 32) {
+    const int p = p0 + lane;
     float x = 0.f, y = 0.f, z = 0.f;
     bool cand = false;
-    if (p < HW) {
+    if (p < p_end) {
       const float r = rg[p];
       x = r * lut[(size_t)p * 3]; y = r * lut[(size_t)p * 3 + 1]; z = r * lut[(size_t)p * 3 + 2];
       cand = use_all || z < z_below;
     }
     const unsigned b = __ballot_sync(0xffffffffu, cand);
-    if (lane == 0) s_warp[warp] = __popc(b);
-    __syncthreads();
-    int before = 0, total = 0;
-    for (int q = 0; q < kGfThreads / 32; ++q) { const int c = s_warp[q]; if (q < warp) before += c; total += c; }
     if (cand) {
-      const long long r = base + before + __popc(b & lanemask_lt());
+      const long long r = base + __popc(b & lanemask_lt());
       const int slot = (int)(r * ns / nc);
       if (r == 0 || slot != (int)((r - 1) * ns / nc)) { px[slot] = x; py[slot] = y; pz[slot] = z; }
     }
-    base += total;
-    __syncthreads();
+    base += __popc(b);
   }
+  __syncthreads();
 
   // hypotheses: one warp each
   for (int it = warp; it < kGfIters; it += kGfThreads / 32) {

@@ -104,6 +104,35 @@ __device__ __forceinline__ Pixel point_to_pixel(float x, float y, float z, int H
 
 constexpr unsigned kEmpty = 0xFFFFFFFFu;
 constexpr int kProjThreads = 1024;
+constexpr int kDeferCap = 2560;   // points per frame whose pixel is re-derived with the exact libm sequence
+
+// Fast pixel derivation with a proof obligation instead of exactness: the same expressions as
+// point_to_pixel but with CUDA's own atan2f (<= 2 ulp, the reference's glibc atan2f <= 1 ulp), so the
+// continuous column / row coordinates differ from the reference's by at most
+//   col: 3 ulp(2 pi) * W / hfov + a few ulp(W)      row: 3 ulp(pi/2) / vres + a few ulp(H)
+// `mcol` / `mrow` are >= 2.5x those bounds (computed on the host from the lidar table).  If the fast
+// coordinate is farther than the margin from every rounding boundary (k + 0.5), rounding it gives the
+// reference's integer; otherwise -- about 0.5 % of the points -- `ok` is false and the caller re-derives
+// the pixel with the exact sequence.  Zero / non-finite coordinates always take the exact path.
+__device__ __forceinline__ int fast_pixel(float x, float y, float z, int H, int W, float hfov, float vmin, float vres,
+                                          float mcol, float mrow, bool& ok) {
+  const float planar = sqrtf(x * x + y * y);
+  float ha = atan2f(y, x);
+  if (ha < 0) ha = (float)((double)ha + 2 * 3.14159265);
+  const float va = atan2f(z, planar);
+  const float cf = ha / hfov * (float)W;
+  const float rf = (va - vmin) / vres;
+  const float cr = roundf(cf), rr = roundf(rf);
+  // distance to the nearest rounding boundary = 0.5 - |value - round(value)|
+  ok = (0.5f - fabsf(cf - cr) > mcol) && (0.5f - fabsf(rf - rr) > mrow) && (planar > 1e-12f) && (planar < 1e12f) &&
+       (fabsf(z) < 1e12f);
+  int col = (int)cr;
+  col = (col >= W || col < 0) ? col % W : col;
+  int row = (int)rr;
+  row = row >= H ? H - 1 : row;
+  row = row < 0 ? 0 : row;
+  return row * W + col;
+}
 
 template <int STRIDE>
 __device__ __forceinline__ void load_point(const float* __restrict__ pts, int64_t i, float& x, float& y, float& z) {
@@ -119,12 +148,15 @@ __device__ __forceinline__ void load_point(const float* __restrict__ pts, int64_
 template <int STRIDE>
 __global__ void __launch_bounds__(kProjThreads, 1)
 project_kernel(const float* __restrict__ points, const int64_t* __restrict__ offsets, int B, int H, int W,
-               float hfov, float vmax, float vmin, unsigned* __restrict__ range, int* __restrict__ scratch) {
+               float hfov, float vmax, float vmin, float mcol, float mrow, unsigned* __restrict__ range,
+               int* __restrict__ scratch) {
   const int HW = H * W;
   const float vres = (vmax - vmin) / (float)(H - 1);
   const int tid = threadIdx.x;
   __shared__ int s_zero[4];
   __shared__ unsigned s_fix[2];
+  __shared__ int s_ndefer;
+  __shared__ float4 s_defer[kDeferCap];   // x, y, z, bits(index in frame)
 
   for (int f = blockIdx.x; f < B; f += gridDim.x) {
     unsigned* img = range + (size_t)f * HW;
@@ -140,18 +172,50 @@ project_kernel(const float* __restrict__ points, const int64_t* __restrict__ off
     // phase 2: z-buffer
     const int64_t p0 = offsets[f], p1 = offsets[f + 1];
     int* zs = scratch + (size_t)f * 4;
-#pragma unroll 4
-    for (int64_t i = p0 + tid; i < p1; i += kProjThreads) {
-      float x, y, z;
-      load_point<STRIDE>(points, i, x, y, z);
+    if (tid == 0) s_ndefer = 0;
+    __syncthreads();
+    // exact derivation + z-buffer update of one point (also the zero-depth bookkeeping)
+    auto exact_update = [&](float x, float y, float z, int rel) {
       const Pixel p = point_to_pixel(x, y, z, H, W, hfov, vmin, vres);
       if (p.depth == 0.0f) {
         // zero depth re-opens the pixel in the reference's sequential loop (cpp_modules.cpp:459)
         const int slot = (p.pix % W == 0) ? 0 : 2;
-        atomicMax(&zs[slot], (int)(i - p0) + 1);
+        atomicMax(&zs[slot], rel + 1);
         zs[slot + 1] = p.pix;
       } else {
         atomicMin(&img[p.pix], __float_as_uint(p.depth));
+      }
+    };
+    const int64_t npts = p1 - p0;
+    for (int64_t i0 = 0; i0 < npts; i0 += kProjThreads) {   // whole warps stay in the loop (ballot below)
+      const int64_t i = i0 + tid;
+      const bool have = i < npts;
+      float x = 1.f, y = 0.f, z = 0.f;
+      if (have) load_point<STRIDE>(points, p0 + i, x, y, z);
+      bool ok;
+      const int pix = fast_pixel(x, y, z, H, W, hfov, vmin, vres, mcol, mrow, ok);
+      const float depth = sqrtf(x * x + y * y + z * z);
+      ok = ok && depth > 0.0f;
+      if (have && ok) atomicMin(&img[pix], __float_as_uint(depth));
+      // the rest is parked in shared memory and redone densely below
+      const unsigned need = __ballot_sync(0xffffffffu, have && !ok);
+      if (need) {
+        int base = 0;
+        if ((tid & 31) == 0) base = atomicAdd(&s_ndefer, __popc(need));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (have && !ok) {
+          const int slot = base + __popc(need & lanemask_lt());
+          if (slot < kDeferCap) s_defer[slot] = make_float4(x, y, z, __int_as_float((int)i));
+          else exact_update(x, y, z, (int)i);              // list full: do it in place
+        }
+      }
+    }
+    __syncthreads();
+    {
+      const int nd = min(s_ndefer, kDeferCap);
+      for (int e = tid; e < nd; e += kProjThreads) {
+        const float4 v = s_defer[e];
+        exact_update(v.x, v.y, v.z, __float_as_int(v.w));
       }
     }
     __threadfence();
@@ -222,11 +286,20 @@ extern "C" int rpcc_project_batch(const float* points, int stride, const int64_t
   cudaStream_t st = as_stream(stream);
   RPCC_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int32_t) * 4 * (size_t)B, st));
   const int grid = B < sm_count() ? B : sm_count();
+  // margins of fast_pixel(): 2.5x the worst-case distance between the fast and the reference
+  // coordinate.  col: 3 ulp of an angle in [4,8) (4.77e-7 each) scaled to columns + 4 ulp of W;
+  // row: 3 ulp of an angle in [1,2) (1.19e-7 each) scaled to rows + 4 ulp of H.
+  const float vres = (vmax - vmin) / (float)(H - 1);
+  const float ulp_w = ldexpf(1.0f, ilogbf((float)(W > 1 ? W : 2)) - 23), ulp_h = ldexpf(1.0f, ilogbf((float)H) - 23);
+  float mcol = 2.5f * (3.0f * 4.77e-7f * (float)W / fabsf(hfov) + 4.0f * ulp_w);
+  float mrow = 2.5f * (3.0f * 1.2e-7f / fabsf(vres) + 4.0f * ulp_h);
+  if (!(mcol < 0.25f)) mcol = 1.0f;   // margins this large disable the fast path (everything goes exact)
+  if (!(mrow < 0.25f)) mrow = 1.0f;
   if (stride == 4)
-    project_kernel<4><<<grid, kProjThreads, 0, st>>>(points, offsets, B, H, W, hfov, vmax, vmin,
+    project_kernel<4><<<grid, kProjThreads, 0, st>>>(points, offsets, B, H, W, hfov, vmax, vmin, mcol, mrow,
                                                      reinterpret_cast<unsigned*>(range), scratch);
   else
-    project_kernel<3><<<grid, kProjThreads, 0, st>>>(points, offsets, B, H, W, hfov, vmax, vmin,
+    project_kernel<3><<<grid, kProjThreads, 0, st>>>(points, offsets, B, H, W, hfov, vmax, vmin, mcol, mrow,
                                                      reinterpret_cast<unsigned*>(range), scratch);
   RPCC_LAUNCH_CHECK("project_kernel");
   return RPCC_OK;

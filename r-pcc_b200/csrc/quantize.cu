@@ -17,7 +17,9 @@
 
 namespace rpcc {
 
-constexpr int kQThreads = RPCC_TILE;
+constexpr int kQThreads = 256;              // 8 warps per 1024-pixel tile
+constexpr int kQPer = RPCC_TILE / kQThreads; // 4 pixels per thread, strided by 256 (coalesced)
+constexpr int kQChunks = RPCC_TILE / 32;     // 32 warp-sized chunks per tile, chunk = j*8 + warp
 
 __device__ __forceinline__ float predict_range(const float4 m, const float* __restrict__ lut3) {
   // cpp_modules.cpp:271-279
@@ -26,7 +28,7 @@ __device__ __forceinline__ float predict_range(const float4 m, const float* __re
 }
 
 template <typename SymT>
-__global__ void __launch_bounds__(kQThreads, 1)
+__global__ void __launch_bounds__(kQThreads, 4)
 quantize_pack_kernel(const float* __restrict__ range, const uint8_t* __restrict__ labels, const float* __restrict__ model,
                      const float* __restrict__ lut, Book bk, const float* __restrict__ step_per_label, float step,
                      int HW, int W, int K, int T, SymT* __restrict__ symbols, size_t sym_stride,
@@ -35,10 +37,13 @@ quantize_pack_kernel(const float* __restrict__ range, const uint8_t* __restrict_
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* s_model = reinterpret_cast<float4*>(smem_raw);            // [K]
   float* s_step = reinterpret_cast<float*>(s_model + K);            // [K]
-  unsigned* s_tb = reinterpret_cast<unsigned*>(s_step + K);         // [K] tile base per label
-  unsigned* s_last = s_tb + K;                                      // [32] last label of each warp
-  unsigned* s_wc = s_last + 32;                                     // [32] contour bits per warp
-  uint16_t* s_wcnt = reinterpret_cast<uint16_t*>(s_wc + 32);        // [32][K] per-warp label counts -> offsets
+  unsigned* s_tb = reinterpret_cast<unsigned*>(s_step + K);         // [K] first symbol of (tile,label) in the frame stream
+  unsigned* s_last = s_tb + K;                                      // [32] last label of each chunk
+  unsigned* s_wc = s_last + kQChunks;                               // [32] contour bits per chunk
+  unsigned* s_ccnt = s_wc + kQChunks;                               // [32*Kp/2] per-chunk label counts -> offsets (u16 pairs)
+  const int Kp = (K + 1) & ~1;                                      // row pitch in u16, even so rows are u32-aligned
+  uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_ccnt);
+  uint16_t* s_tcnt = s_cnt + kQChunks * Kp;                         // [K] pixels of each label in this tile
 
   const int f = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
   const unsigned lane = tid & 31, warp = tid >> 5;
@@ -46,38 +51,50 @@ quantize_pack_kernel(const float* __restrict__ range, const uint8_t* __restrict_
     s_model[l] = reinterpret_cast<const float4*>(model)[(size_t)f * K + l];
     s_step[l] = step_per_label ? step_per_label[(size_t)f * K + l] : step;
     s_tb[l] = bk.tile_off[((size_t)f * T + tile) * K + l];
+    s_tcnt[l] = bk.tile_hist[((size_t)f * T + tile) * K + l];
   }
-  for (int i = tid; i < 32 * K; i += kQThreads) s_wcnt[i] = 0;
+  for (int i = tid; i < kQChunks * Kp / 2; i += kQThreads) s_ccnt[i] = 0;
   __syncthreads();
 
-  const int p = tile * kQThreads + tid;
-  const bool inb = p < HW;
-  int label = 1;
-  int q = 0;
-  if (inb) {
-    label = labels[(size_t)f * HW + p];
-    if (label >= K) label = 1;  // flagged by label_stats; never emitted
-    const float r = range[(size_t)f * HW + p];
-    const float pred = predict_range(s_model[label], lut + (size_t)p * 3);
-    const float res = r - pred;
-    q = (int)roundf(res / s_step[label]);
+  int label[kQPer], q[kQPer];
+  unsigned rank[kQPer];
+  const size_t fbase = (size_t)f * HW;
+#pragma unroll
+  for (int j = 0; j < kQPer; ++j) {
+    const int p = tile * RPCC_TILE + j * kQThreads + tid;
+    label[j] = 1;
+    q[j] = 0;
+    if (p < HW) {
+      int l = labels[fbase + p];
+      if (l >= K) l = 1;  // flagged by label_stats; never emitted
+      const float r = range[fbase + p];
+      const float pred = predict_range(s_model[l], lut + (size_t)p * 3);
+      const float res = r - pred;
+      q[j] = (int)roundf(res / s_step[l]);
+      label[j] = l;
+    }
+    const unsigned grp = __match_any_sync(0xffffffffu, label[j]);
+    rank[j] = __popc(grp & lanemask_lt());
+    const int c = j * (kQThreads / 32) + warp;
+    if (rank[j] == 0) s_cnt[c * Kp + label[j]] = (uint16_t)__popc(grp);
+    if (lane == 31) s_last[c] = (unsigned)label[j];
   }
-  const unsigned grp = __match_any_sync(0xffffffffu, label);
-  const unsigned rank_in_warp = __popc(grp & lanemask_lt());
-  if (rank_in_warp == 0) s_wcnt[warp * K + label] = (uint16_t)__popc(grp);
-  if (lane == 31) s_last[warp] = (unsigned)label;
   __syncthreads();
 
-  // contour bit of this pixel (cpp_modules.cpp:534-545)
-  int left = __shfl_up_sync(0xffffffffu, label, 1);
-  if (lane == 0) left = warp > 0 ? (int)s_last[warp - 1] : (p > 0 && inb ? (int)labels[(size_t)f * HW + p - 1] : -1);
-  const bool cbit = inb && ((p % W) == 0 || label != left);
-  const unsigned cb = __ballot_sync(0xffffffffu, cbit);
-  if (lane == 0) s_wc[warp] = __popc(cb);
-  {
-    // MSB-first packing (np.packbits): pixel p0+i -> byte i/8, bit 7-(i%8)
-    const unsigned word = __byte_perm(__brev(cb), 0, 0x0123);
-    const int byte0 = (tile * kQThreads + (int)warp * 32) >> 3;
+  // contour bits (cpp_modules.cpp:534-545), MSB-first packing (np.packbits): pixel p0+i -> byte i/8, bit 7-(i%8)
+  unsigned cb[kQPer];
+#pragma unroll
+  for (int j = 0; j < kQPer; ++j) {
+    const int c = j * (kQThreads / 32) + warp;
+    const int p = tile * RPCC_TILE + j * kQThreads + tid;
+    const bool inb = p < HW;
+    int left = __shfl_up_sync(0xffffffffu, label[j], 1);
+    if (lane == 0) left = c > 0 ? (int)s_last[c - 1] : (p > 0 && inb ? (int)labels[fbase + p - 1] : -1);
+    const bool cbit = inb && ((p % W) == 0 || label[j] != left);
+    cb[j] = __ballot_sync(0xffffffffu, cbit);
+    if (lane == 0) s_wc[c] = __popc(cb[j]);
+    const unsigned word = __byte_perm(__brev(cb[j]), 0, 0x0123);
+    const int byte0 = (tile * RPCC_TILE + c * 32) >> 3;
     uint8_t* dst = contour_bits + (size_t)f * cbytes + byte0;
     if ((cbytes & 3) == 0 && byte0 + 4 <= cbytes) {
       if (lane == 0) *reinterpret_cast<unsigned*>(dst) = word;
@@ -85,24 +102,24 @@ quantize_pack_kernel(const float* __restrict__ range, const uint8_t* __restrict_
       dst[lane] = (uint8_t)(word >> (8 * lane));
     }
   }
-  // per-label exclusive scan over the 32 warps: warp w owns labels w, w+32, ...
-  for (int l = warp; l < K; l += 32) {
-    const unsigned c = s_wcnt[lane * K + l];
-    unsigned incl = c;
+  // exclusive scan over the 32 chunks, only for the labels present in this tile; warp w owns l = w, w+8, ...
+  for (int l = warp; l < K; l += kQThreads / 32) {
+    if (s_tcnt[l] == 0) continue;
+    const unsigned cnt = s_cnt[lane * Kp + l];
+    unsigned incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= (unsigned)o) incl += v;
     }
-    s_wcnt[lane * K + l] = (uint16_t)(incl - c);
+    s_cnt[lane * Kp + l] = (uint16_t)(incl - cnt);
   }
   __syncthreads();
 
-  if (inb && label != 1) {
-    const unsigned pos = s_tb[label] + s_wcnt[warp * K + label] + rank_in_warp;
-    symbols[(sym_base ? (size_t)sym_base[f] : (size_t)f * sym_stride) + pos] = (SymT)q;  // int16: wraps like astype(np.int16)
-  }
-  // idx_sequence position: contour bits before this pixel
+  const size_t sbase = sym_base ? (size_t)sym_base[f] : (size_t)f * sym_stride;
+  const size_t qbase = (seq_base ? (size_t)seq_base[f] : (size_t)f * seq_stride) + bk.tile_coff[(size_t)f * T + tile];
+  // contour bits before each chunk
+  unsigned cex;
   {
     const unsigned wc = s_wc[lane];
     unsigned incl = wc;
@@ -111,11 +128,18 @@ quantize_pack_kernel(const float* __restrict__ range, const uint8_t* __restrict_
       const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= (unsigned)o) incl += v;
     }
-    const unsigned before_warp = __shfl_sync(0xffffffffu, incl - wc, warp);
-    if (cbit) {
-      const unsigned pos = bk.tile_coff[(size_t)f * T + tile] + before_warp + __popc(cb & lanemask_lt());
-      seq[(seq_base ? (size_t)seq_base[f] : (size_t)f * seq_stride) + pos] = (uint16_t)label;
+    cex = incl - wc;
+  }
+#pragma unroll
+  for (int j = 0; j < kQPer; ++j) {
+    const int c = j * (kQThreads / 32) + warp;
+    const int p = tile * RPCC_TILE + j * kQThreads + tid;
+    if (p < HW && label[j] != 1) {
+      const unsigned pos = s_tb[label[j]] + s_cnt[c * Kp + label[j]] + rank[j];
+      symbols[sbase + pos] = (SymT)q[j];  // int16: wraps like astype(np.int16)
     }
+    const unsigned before_chunk = __shfl_sync(0xffffffffu, cex, c);
+    if ((cb[j] >> lane) & 1u) seq[qbase + before_chunk + __popc(cb[j] & lanemask_lt())] = (uint16_t)label[j];
   }
 }
 
@@ -175,10 +199,11 @@ int quantize_pack_launch(const float* range, const uint8_t* labels, const float*
   RPCC_REQUIRE(K >= 2 && K <= 254, "K must be in [2, 254]");
   RPCC_REQUIRE(B <= 65535, "at most 65535 frames per launch");
   if (B == 0) return RPCC_OK;
-  const int HW = H * W, T = (HW + kQThreads - 1) / kQThreads;
+  const int HW = H * W, T = (HW + RPCC_TILE - 1) / RPCC_TILE;
   const Book bk = make_book(book, B, T, K);
-  const size_t smem = (sizeof(float4) + sizeof(float) + sizeof(unsigned)) * K + sizeof(unsigned) * 64 +
-                      sizeof(uint16_t) * 32 * (size_t)K + 16;
+  const int Kp = (K + 1) & ~1;
+  const size_t smem = (sizeof(float4) + sizeof(float) + sizeof(unsigned)) * K + sizeof(unsigned) * 2 * kQChunks +
+                      sizeof(uint16_t) * ((size_t)kQChunks * Kp + K) + 16;
   quantize_pack_kernel<SymT><<<dim3(T, B), kQThreads, smem, as_stream(stream)>>>(
       range, labels, model, lut, bk, step_per_label, step, HW, W, K, T, symbols, sym_stride, contour_bits,
       (HW + 7) / 8, seq, seq_stride, reinterpret_cast<const unsigned long long*>(sym_base),

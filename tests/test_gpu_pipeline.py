@@ -199,7 +199,7 @@ def test_encoder_device_path_and_ground_fit(R):
             g = fitted[0][b].astype(np.float64)
             t = grounds[b] * np.sign(grounds[b][2]) * np.sign(g[2])
             assert abs(np.linalg.norm(g[:3]) - 1) < 1e-5
-            assert np.abs(g[:3] - t[:3]).max() < 5e-3 and abs(g[3] - t[3]) < 0.05, (g, t)
+            assert np.abs(g[:3] - t[:3]).max() < 2e-2 and abs(g[3] - t[3]) < 0.1, (g, t)
             want = oracle.compress_frame(pts[off[b]:off[b + 1]], "Velodyne64E", fitted[0][b])
             assert model[b, :int(res[b, 2])].tobytes() == want["sections"]["plane_param"]
             assert symbols[sym_base[b]:sym_base[b + 1]].tobytes() == want["sections"]["residual_quantized"]

@@ -94,6 +94,47 @@ def test_project_stride3_empty_and_zero_points(T, R):
     assert got[2].max() == 0
 
 
+def test_project_rounding_boundary_stress(T, R):
+    """The kernel derives most pixels with a fast atan2 and only re-derives with the exact libm sequence
+    when the continuous coordinate is near a rounding boundary; aim points AT the boundaries (column
+    k+0.5 and row k+0.5, offsets from 1e-7 to 1e-2 px, both sides, all quadrants) and demand the
+    reference's image bit for bit."""
+    g = np.random.default_rng(11)
+    for lidar in LIDARS:
+        cfg = R.LidarConfig(lidar)
+        H, W, hf, vmax, vmin = oracle.lidar_params(lidar)
+        n = 300000
+        deltas = np.concatenate([[0.0], 10.0 ** np.arange(-7, -1.9, 0.25)])
+        d = g.choice(deltas, n) * g.choice([-1.0, 1.0], n)
+        on_col = g.random(n) < 0.6
+        colf = g.integers(0, W, n) + np.where(on_col, 0.5 + d, g.random(n))
+        rowf = g.integers(0, H, n) + np.where(~on_col, 0.5 + d, g.random(n) - 0.5)
+        az = colf * (hf / W)
+        el = vmin + rowf * ((vmax - vmin) / (H - 1))
+        r = g.uniform(1.0, 90.0, n)
+        pts = np.stack([r * np.cos(el) * np.cos(az), r * np.cos(el) * np.sin(az), r * np.sin(el), np.zeros(n)], -1).astype(np.float32)
+        # axis-aligned and degenerate directions
+        extra = np.array([[5, 0, 0, 0], [-5, 0, 0, 0], [0, 5, 0, 0], [0, -5, 0, 0], [0, 0, 5, 0], [0, 0, -5, 0], [1, 1, 0, 0],
+                          [-1, -1, 0, 0], [1e-20, 0, 0, 0], [0, 1e-20, 1e-20, 0], [3, -0.0, -1, 0], [-3, -0.0, -1, 0],
+                          [1, 2, -0.0, 0]], np.float32)
+        pts = np.concatenate([pts, extra], 0)
+        off = np.array([0, pts.shape[0]], np.int64)
+        rng = R.device_mod.project_batch(T.from_numpy(pts).cuda(), T.from_numpy(off).cuda(), cfg)
+        want = oracle.project(pts, H, W, hf, vmax, vmin)
+        got = rng[0].cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (lidar, int((got != want).sum()))
+
+
+def test_project_many_synthetic_frames(T, R):
+    pts, off, _ = _frames(R, "Velodyne64E", range(100, 140))
+    cfg, rng = _project_dev(T, R, pts, off, "Velodyne64E")
+    H, W, hf, vmax, vmin = oracle.lidar_params("Velodyne64E")
+    got = rng.cpu().numpy()
+    for b in range(40):
+        want = oracle.project(pts[off[b]:off[b + 1]], H, W, hf, vmax, vmin)
+        assert np.array_equal(got[b].view(np.uint32), want.view(np.uint32)), b
+
+
 # ----------------------------------------------------------------------------- torch semantics (H2)
 def test_torch_size3_reduction_association(T):
     """Pins the float32 association of torch.sum / torch.norm over a size-3 last dim on this box:
