@@ -35,10 +35,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=1024, help="frames per step per GPU")
+    ap.add_argument("--frames", type=int, default=1184, help="frames per step per GPU (default 4 x 296)")
     ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic frames generated per GPU")
-    ap.add_argument("--max-batch", type=int, default=256, help="frames per kernel launch")
-    ap.add_argument("--e2e-frames", type=int, default=512)
+    ap.add_argument("--max-batch", type=int, default=296, help="frames per kernel launch (2 x 148 SMs)")
+    ap.add_argument("--e2e-frames", type=int, default=592)
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -21,11 +21,7 @@
 //    in shared memory), builds the masked point cloud straight from range x LUT, keeps a single
 //    representative of the identical origin points (ground / empty pixels) per residue class,
 //    and exchanges the per-CTA winners through distributed shared memory once per round.
-#include <cooperative_groups.h>
-
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace rpcc {
 
@@ -100,10 +96,48 @@ fps_generic_kernel(const float* __restrict__ points, int n, int m, int log2bs, f
 // ------------------------------------------------------------------------------------------------
 constexpr int kCl = 8;            // CTAs per cluster
 constexpr int kFpsThreads = 1024; // = the reference's block size, so thread id == residue class k mod 1024
-constexpr int kRegSlots = 6;      // candidate points per thread kept in registers; the rest in shared memory
+constexpr int kRegSlots = 6;      // candidate points per thread also kept in registers (all are mirrored in smem)
+constexpr unsigned kRecBytes = 32;
 
-// one candidate: squared distance (as ordered bits), tie key, coordinates
-struct __align__(16) FpsRecord { unsigned d, tk; float x, y; float z; int pad0, pad1, pad2; };
+// ---- raw shared-memory / cluster / mbarrier primitives (sm_90+ PTX)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float lds_f32(unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ unsigned lds_u8(unsigned a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds_v4(unsigned a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_u8(unsigned a, unsigned v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_v4(unsigned a, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ unsigned mapa_u32(unsigned a, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_init(unsigned a, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned a, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned a, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  } while (!ok);
+}
+// 16 bytes into a peer CTA's shared memory; the peer's mbarrier is credited with the bytes when they land
+__device__ __forceinline__ void st_async_v4(unsigned raddr, uint4 v, unsigned rmbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];"
+               ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rmbar) : "memory");
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.aligned;\n barrier.cluster.wait.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 
 // torch float32 semantics of utils/segment_utils.py:137-139 for one pixel:
 // |sum(pc*g)+g3| / norm(g) > thr ? pc : 0   (size-3 reductions associate as torch_sum3)
@@ -116,37 +150,44 @@ __device__ __forceinline__ void masked_point(float r, const float* __restrict__ 
 }
 
 // winner among the lanes of a warp: max d (bit pattern of a non-negative float), then min tie key.
-// Returns the owning lane (every lane gets the same answer); lanes without a candidate pass d = 0, tk = ~0.
+// Returns the owning lane (same answer in every lane); lanes without a candidate pass d = 0, tk = ~0.
 __device__ __forceinline__ int warp_winner(unsigned d, unsigned tk, unsigned& dmax, unsigned& tkmin) {
   dmax = __reduce_max_sync(0xffffffffu, d);
   const unsigned t = d == dmax ? tk : 0xFFFFFFFFu;
   tkmin = __reduce_min_sync(0xffffffffu, t);
-  const unsigned own = __ballot_sync(0xffffffffu, t == tkmin);
-  return __ffs(own) - 1;
+  return __ffs(__ballot_sync(0xffffffffu, t == tkmin)) - 1;
 }
 
+// Shared-memory map (bytes):  [0,1024) per-warp winners 2 x 32 x 16
+//                             [1024,1536) per-CTA winners 2 x 8 x 32 (written by the peers, st.async)
+//                             [1536,1552) two mbarriers
+//                             [2048, ...) point slots: x[SLOTS][1024], y, z (f32) then row[SLOTS][1024] (u8)
 template <int SLOTS>
 __global__ void __launch_bounds__(kFpsThreads, 1)
 segment_fps_kernel(const float* __restrict__ range, const float* __restrict__ lut, const float* __restrict__ ground,
                    int B, int HW, int m, float thr, int* __restrict__ center_idx, float* __restrict__ centers) {
-  cg::cluster_group cluster = cg::this_cluster();
-  const int rank = (int)cluster.block_rank();
+  const unsigned rank = cluster_ctarank();
   const int ncluster = gridDim.x / kCl;
   const int cid = blockIdx.x / kCl;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int RS = SLOTS < kRegSlots ? SLOTS : kRegSlots;  // register slots
-  constexpr int SM = SLOTS - RS;                             // shared-memory slots
+  constexpr int RS = SLOTS < kRegSlots ? SLOTS : kRegSlots;
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  FpsRecord* s_part = reinterpret_cast<FpsRecord*>(smem_raw);                 // [2][32] per-warp winners
-  FpsRecord* s_rec = s_part + 64;                                             // [2][kCl] per-CTA winners (written remotely)
-  float* sx = reinterpret_cast<float*>(s_rec + 2 * kCl);                      // [SM][1024]
-  float* sy = sx + SM * kFpsThreads;
-  float* sz = sy + SM * kFpsThreads;
-  unsigned char* sj = reinterpret_cast<unsigned char*>(sz + SM * kFpsThreads);  // [SLOTS][1024] row (k >> 10) of each slot
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const unsigned sbase = smem_u32(smem_raw);
+  const unsigned a_part = sbase, a_rec = sbase + 1024, a_bar = sbase + 1536;
+  constexpr unsigned kPlane = SLOTS * kFpsThreads * 4;
+  const unsigned a_x = sbase + 2048 + tid * 4, a_y = a_x + kPlane, a_z = a_y + kPlane;   // + slot * 4096
+  const unsigned a_j = sbase + 2048 + 3 * kPlane + tid;                                  // + slot * 1024
+
+  if (tid == 0) {
+    mbar_init(a_bar, 1);
+    mbar_init(a_bar + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster_barrier();   // peers may now signal our mbarriers
 
   const unsigned tie_hi = __brev((unsigned)tid) & 0xFFC00000u;  // bitrev10(tid) in the top 10 bits
-  unsigned par = 0;
+  unsigned round = 0;                                            // rounds since kernel start (buffer / phase bookkeeping)
 
   for (int f = cid; f < B; f += ncluster) {
     const float* rg = range + (size_t)f * HW;
@@ -156,7 +197,8 @@ segment_fps_kernel(const float* __restrict__ range, const float* __restrict__ lu
     // ---- gather: CTA `rank` owns the rows j = rank, rank+8, ... of the reference's (row j, thread tid)
     //      layout k = j*1024 + tid.  Kept per thread, in increasing k: every non-origin point and the
     //      first origin point (ground / empty pixels are all the same point; the first one carries the
-    //      best tie key of its residue class inside this CTA).
+    //      best tie key of its residue class inside this CTA).  Unused slots get temp = 0: they can never
+    //      exceed a running maximum, so the round loop needs no per-lane guard.
     float rx[RS], ry[RS], rz[RS];
 #pragma unroll
     for (int s = 0; s < RS; ++s) { rx[s] = 0.f; ry[s] = 0.f; rz[s] = 0.f; }
@@ -164,7 +206,7 @@ segment_fps_kernel(const float* __restrict__ range, const float* __restrict__ lu
     bool origin_seen = false;
 #pragma unroll 4
     for (int jj = 0; jj < SLOTS; ++jj) {
-      const int j = jj * kCl + rank;
+      const int j = jj * kCl + (int)rank;
       const int k = j * kFpsThreads + tid;
       if (k < HW) {
         float x, y, z;
@@ -172,14 +214,10 @@ segment_fps_kernel(const float* __restrict__ range, const float* __restrict__ lu
         const bool origin = (x == 0.f) && (y == 0.f) && (z == 0.f);
         if (!(origin && origin_seen)) {
           origin_seen = origin_seen || origin;
-          if (mine < RS) {
 #pragma unroll
-            for (int s = 0; s < RS; ++s) if (mine == s) { rx[s] = x; ry[s] = y; rz[s] = z; }
-          } else {
-            const int o = (mine - RS) * kFpsThreads + tid;
-            sx[o] = x; sy[o] = y; sz[o] = z;
-          }
-          sj[mine * kFpsThreads + tid] = (unsigned char)j;
+          for (int s = 0; s < RS; ++s) if (mine == s) { rx[s] = x; ry[s] = y; rz[s] = z; }
+          sts_f32(a_x + mine * 4096, x); sts_f32(a_y + mine * 4096, y); sts_f32(a_z + mine * 4096, z);
+          sts_u8(a_j + mine * 1024, (unsigned)j);
           ++mine;
         }
       }
@@ -190,7 +228,7 @@ segment_fps_kernel(const float* __restrict__ range, const float* __restrict__ lu
 
     float temp[SLOTS];
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s) temp[s] = 1e10f;
+    for (int s = 0; s < SLOTS; ++s) temp[s] = s < mine ? 1e10f : 0.0f;
 
     // seed 0 is flat index 0 (sampling_gpu.cu:44-46)
     float x1, y1, z1;
@@ -201,70 +239,70 @@ segment_fps_kernel(const float* __restrict__ range, const float* __restrict__ lu
     }
 
     for (int j = 1; j < m; ++j) {
-      par ^= 1u;
+      const unsigned par = round & 1u, phase = (round >> 1) & 1u;
+      ++round;
+      if (tid == 0) mbar_expect_tx(a_bar + par * 8, kCl * kRecBytes);
       float best = -1.f;
       int bs = 0;
 #pragma unroll
       for (int s = 0; s < SLOTS; ++s) {
-        if (s >= wmax) break;  // warp-uniform
-        if (s < mine) {
-          float px, py, pz;
-          if (s < RS) { px = rx[s < RS ? s : 0]; py = ry[s < RS ? s : 0]; pz = rz[s < RS ? s : 0]; }
-          else { const int o = (s - RS) * kFpsThreads + tid; px = sx[o]; py = sy[o]; pz = sz[o]; }
-          const float d2 = fminf(fps_dist(px, py, pz, x1, y1, z1), temp[s]);
-          temp[s] = d2;
-          if (d2 > best) { best = d2; bs = s; }
-        }
+        if (s >= RS && s >= wmax) break;  // warp-uniform
+        float px, py, pz;
+        if (s < RS) { px = rx[s < RS ? s : 0]; py = ry[s < RS ? s : 0]; pz = rz[s < RS ? s : 0]; }
+        else { px = lds_f32(a_x + s * 4096); py = lds_f32(a_y + s * 4096); pz = lds_f32(a_z + s * 4096); }
+        const float d2 = fminf(fps_dist(px, py, pz, x1, y1, z1), temp[s]);
+        temp[s] = d2;
+        if (d2 > best) { best = d2; bs = s; }
       }
-      // ---- warp winner -> shared
+      // ---- warp winner -> shared (16 bytes: d, tie key, slot)
       {
         const unsigned d = mine > 0 ? __float_as_uint(best) : 0u;
-        // the tie key (one shared-memory read) is only needed by lanes that hold the warp maximum
         const unsigned dmax = __reduce_max_sync(0xffffffffu, d);
-        const unsigned tk = (mine > 0 && d == dmax) ? (tie_hi | (unsigned)sj[bs * kFpsThreads + tid]) : 0xFFFFFFFFu;
+        // the tie key (one shared-memory read) is only needed by lanes that hold the warp maximum
+        const unsigned tk = (mine > 0 && d == dmax) ? (tie_hi | lds_u8(a_j + bs * 1024)) : 0xFFFFFFFFu;
         const unsigned tkmin = __reduce_min_sync(0xffffffffu, tk);
-        const int own = __ffs(__ballot_sync(0xffffffffu, tk == tkmin)) - 1;
-        if (lane == own) {
-          FpsRecord rec;
-          rec.d = dmax; rec.tk = tkmin; rec.pad0 = 0; rec.pad1 = 0; rec.pad2 = 0;
-          rec.x = 0.f; rec.y = 0.f; rec.z = 0.f;
-          if (tkmin != 0xFFFFFFFFu) {
-            if (bs < RS) {
-#pragma unroll
-              for (int s = 0; s < RS; ++s) if (bs == s) { rec.x = rx[s]; rec.y = ry[s]; rec.z = rz[s]; }
-            } else {
-              const int o = (bs - RS) * kFpsThreads + tid;
-              rec.x = sx[o]; rec.y = sy[o]; rec.z = sz[o];
-            }
-          }
-          s_part[par * 32 + warp] = rec;
-        }
+        if (tk == tkmin && (tk != 0xFFFFFFFFu || lane == 0))
+          sts_v4(a_part + (par * 32 + warp) * 16, make_uint4(dmax, tkmin, (unsigned)bs, 0u));
       }
       __syncthreads();
-      // ---- CTA winner: warp 0 only, published to every CTA of the cluster through DSMEM
+      // ---- CTA winner: warp 0 only; its coordinates come from the shared mirror; published to every CTA
+      //      of the cluster with st.async, which credits the receiver's mbarrier
       if (warp == 0) {
-        const FpsRecord mineRec = s_part[par * 32 + lane];
+        const uint4 pr = lds_v4(a_part + (par * 32 + lane) * 16);
         unsigned dmax, tkmin;
-        const int own = warp_winner(mineRec.d, mineRec.tk, dmax, tkmin);
+        const int own = warp_winner(pr.x, pr.y, dmax, tkmin);
         if (lane == own) {
+          float wx = 0.f, wy = 0.f, wz = 0.f;
+          if (tkmin != 0xFFFFFFFFu) {
+            const unsigned t = __brev(tkmin & 0xFFC00000u);           // owning thread
+            const unsigned o = pr.z * 4096 + t * 4 - tid * 4;         // a_x is relative to this thread
+            wx = lds_f32(a_x + o); wy = lds_f32(a_y + o); wz = lds_f32(a_z + o);
+          }
+          const uint4 r0 = make_uint4(dmax, tkmin, __float_as_uint(wx), __float_as_uint(wy));
+          const uint4 r1 = make_uint4(__float_as_uint(wz), 0u, 0u, 0u);
+          const unsigned dst = a_rec + (par * kCl + rank) * kRecBytes;
 #pragma unroll
-          for (int r = 0; r < kCl; ++r) {
-            FpsRecord* dst = cluster.map_shared_rank(s_rec, r) + par * kCl + rank;
-            *dst = mineRec;
+          for (unsigned r = 0; r < kCl; ++r) {
+            const unsigned rd = mapa_u32(dst, r), rb = mapa_u32(a_bar + par * 8, r);
+            st_async_v4(rd, r0, rb);
+            st_async_v4(rd + 16, r1, rb);
           }
         }
       }
-      cluster.sync();
+      mbar_wait(a_bar + par * 8, phase);
       // ---- cluster winner: every warp reduces the 8 records on its own
       {
-        FpsRecord w;
-        w.d = 0u; w.tk = 0xFFFFFFFFu; w.x = 0.f; w.y = 0.f; w.z = 0.f;
-        if (lane < kCl) w = s_rec[par * kCl + lane];
+        uint4 w = make_uint4(0u, 0xFFFFFFFFu, 0u, 0u);
+        float wz = 0.f;
+        if (lane < kCl) {
+          w = lds_v4(a_rec + (par * kCl + lane) * kRecBytes);
+          wz = lds_f32(a_rec + (par * kCl + lane) * kRecBytes + 16);
+        }
         unsigned dmax, tkmin;
-        const int own = warp_winner(w.d, w.tk, dmax, tkmin);
-        x1 = __shfl_sync(0xffffffffu, w.x, own);
-        y1 = __shfl_sync(0xffffffffu, w.y, own);
-        z1 = __shfl_sync(0xffffffffu, w.z, own);
+        const int own = warp_winner(w.x, w.y, dmax, tkmin);
+        x1 = __uint_as_float(__shfl_sync(0xffffffffu, w.z, own));
+        y1 = __uint_as_float(__shfl_sync(0xffffffffu, w.w, own));
+        z1 = __shfl_sync(0xffffffffu, wz, own);
         if (rank == 0 && tid == 0) {
           const int k = (int)(((tkmin & 0x3FFFFFu) << 10) | (__brev(tkmin & 0xFFC00000u)));
           center_idx[(size_t)f * m + j] = k;
@@ -276,12 +314,12 @@ segment_fps_kernel(const float* __restrict__ range, const float* __restrict__ lu
     // the next frame's gather rewrites the shared slots: every thread must have left the round loop
     __syncthreads();
   }
+  cluster_barrier();   // no peer may still be writing into this CTA's shared memory when it exits
 }
 
 template <int SLOTS>
 static size_t fps_smem_bytes() {
-  constexpr int RS = SLOTS < kRegSlots ? SLOTS : kRegSlots;
-  return (size_t)(SLOTS - RS) * kFpsThreads * 12 + (size_t)SLOTS * kFpsThreads + (64 + 2 * kCl) * sizeof(FpsRecord);
+  return 2048 + (size_t)SLOTS * kFpsThreads * 13;
 }
 
 template <int SLOTS>
@@ -340,7 +378,6 @@ extern "C" int rpcc_segment_fps_batch(const float* range, const float* lut, cons
   if (need <= 4) return launch_segment_fps<4>(range, lut, ground, B, HW, m, ground_thr, center_idx, centers, st);
   if (need <= 10) return launch_segment_fps<10>(range, lut, ground, B, HW, m, ground_thr, center_idx, centers, st);
   if (need <= 16) return launch_segment_fps<16>(range, lut, ground, B, HW, m, ground_thr, center_idx, centers, st);
-  if (need <= 20) return launch_segment_fps<20>(range, lut, ground, B, HW, m, ground_thr, center_idx, centers, st);
-  set_error("rpcc_segment_fps_batch: H*W = %d exceeds the on-chip capacity (163840 pixels)", HW);
+  set_error("rpcc_segment_fps_batch: H*W = %d exceeds the on-chip capacity (131072 pixels)", HW);
   return RPCC_ERR_CAPACITY;
 }

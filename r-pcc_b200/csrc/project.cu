@@ -106,31 +106,53 @@ constexpr unsigned kEmpty = 0xFFFFFFFFu;
 constexpr int kProjThreads = 1024;
 constexpr int kDeferCap = 2560;   // points per frame whose pixel is re-derived with the exact libm sequence
 
-// Fast pixel derivation with a proof obligation instead of exactness: the same expressions as
-// point_to_pixel but with CUDA's own atan2f (<= 2 ulp, the reference's glibc atan2f <= 1 ulp), so the
-// continuous column / row coordinates differ from the reference's by at most
-//   col: 3 ulp(2 pi) * W / hfov + a few ulp(W)      row: 3 ulp(pi/2) / vres + a few ulp(H)
-// `mcol` / `mrow` are >= 2.5x those bounds (computed on the host from the lidar table).  If the fast
-// coordinate is farther than the margin from every rounding boundary (k + 0.5), rounding it gives the
-// reference's integer; otherwise -- about 0.5 % of the points -- `ok` is false and the caller re-derives
-// the pixel with the exact sequence.  Zero / non-finite coordinates always take the exact path.
-__device__ __forceinline__ int fast_pixel(float x, float y, float z, int H, int W, float hfov, float vmin, float vres,
-                                          float mcol, float mrow, bool& ok) {
-  const float planar = sqrtf(x * x + y * y);
-  float ha = atan2f(y, x);
-  if (ha < 0) ha = (float)((double)ha + 2 * 3.14159265);
-  const float va = atan2f(z, planar);
-  const float cf = ha / hfov * (float)W;
-  const float rf = (va - vmin) / vres;
-  const float cr = roundf(cf), rr = roundf(rf);
-  // distance to the nearest rounding boundary = 0.5 - |value - round(value)|
-  ok = (0.5f - fabsf(cf - cr) > mcol) && (0.5f - fabsf(rf - rr) > mrow) && (planar > 1e-12f) && (planar < 1e12f) &&
-       (fabsf(z) < 1e12f);
-  int col = (int)cr;
+// Fast pixel derivation with a proof obligation instead of exactness.  A division-free atan2
+// (degree-17 odd minimax polynomial on [0,1], |error| <= 1.0e-7 rad in f32, plus the quadrant
+// fix-ups) and reciprocal multiplies give continuous column / row coordinates that differ from the
+// reference's (glibc atan2f <= 1 ulp, then IEEE divisions) by at most
+//   col: ~6e-4 px at W = 2000 (7e-7 rad of angle error scaled by W / hfov, a few ulp(W) of rounding)
+//   row: ~6e-5 rows at vres = 0.00745 rad
+// `mcol` / `mrow` (host, from the lidar table) are >= 4x those bounds.  If the fast coordinate is
+// farther than the margin from every rounding boundary (k + 0.5), rounding it gives the reference's
+// integer; otherwise -- under 1 % of the points -- `ok` is false and the caller re-derives the pixel with
+// the exact sequence.  Zero / tiny / huge coordinates always take the exact path.
+__device__ __forceinline__ float fast_atan2(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float t = __fdividef(mn, mx);
+  const float u = __fmul_rn(t, t);
+  float p = 0.002456609858199954f;
+  p = __fmaf_rn(p, u, -0.01440086867660284f);
+  p = __fmaf_rn(p, u, 0.03978036344051361f);
+  p = __fmaf_rn(p, u, -0.07234777510166168f);
+  p = __fmaf_rn(p, u, 0.10498903691768646f);
+  p = __fmaf_rn(p, u, -0.14161217212677002f);
+  p = __fmaf_rn(p, u, 0.19985905289649963f);
+  p = __fmaf_rn(p, u, -0.33332598209381104f);
+  p = __fmaf_rn(p, u, 0.9999998807907104f);
+  float a = __fmul_rn(p, t);
+  a = ay > ax ? 1.5707963705062866f - a : a;
+  a = x < 0.0f ? 3.1415927410125732f - a : a;
+  return copysignf(a, y);
+}
+
+__device__ __forceinline__ int fast_pixel(float x, float y, float z, int H, int W, float col_scale, float vmin,
+                                          float row_scale, float mcol, float mrow, bool& ok) {
+  const float p2 = x * x + y * y;
+  const float planar = __fsqrt_rn(p2);
+  float ha = fast_atan2(y, x);
+  ha = ha < 0.0f ? ha + 6.2831853071795862f : ha;
+  const float va = fast_atan2(z, planar);
+  const float ct = __fmaf_rn(ha, col_scale, 0.5f);          // column coordinate + 0.5
+  const float rt = __fmaf_rn(va - vmin, row_scale, 0.5f);   // row coordinate + 0.5
+  const float cfl = floorf(ct), rfl = floorf(rt);
+  const float cfr = ct - cfl, rfr = rt - rfl;               // distance above the lower rounding boundary
+  const bool row_far = rt < -1.0f || rt > (float)H + 1.0f;  // clamped to the same edge either way
+  ok = (cfr > mcol) && (cfr < 1.0f - mcol) && (row_far || ((rfr > mrow) && (rfr < 1.0f - mrow))) &&
+       (p2 > 1e-24f) && (p2 < 1e24f) && (fabsf(z) < 1e12f);
+  int col = (int)cfl;
   col = (col >= W || col < 0) ? col % W : col;
-  int row = (int)rr;
-  row = row >= H ? H - 1 : row;
-  row = row < 0 ? 0 : row;
+  int row = (int)fminf(fmaxf(rfl, 0.0f), (float)(H - 1));
   return row * W + col;
 }
 
@@ -152,6 +174,7 @@ project_kernel(const float* __restrict__ points, const int64_t* __restrict__ off
                int* __restrict__ scratch) {
   const int HW = H * W;
   const float vres = (vmax - vmin) / (float)(H - 1);
+  const float col_scale = (float)W / hfov, row_scale = 1.0f / vres;
   const int tid = threadIdx.x;
   __shared__ int s_zero[4];
   __shared__ unsigned s_fix[2];
@@ -193,7 +216,7 @@ project_kernel(const float* __restrict__ points, const int64_t* __restrict__ off
       float x = 1.f, y = 0.f, z = 0.f;
       if (have) load_point<STRIDE>(points, p0 + i, x, y, z);
       bool ok;
-      const int pix = fast_pixel(x, y, z, H, W, hfov, vmin, vres, mcol, mrow, ok);
+      const int pix = fast_pixel(x, y, z, H, W, col_scale, vmin, row_scale, mcol, mrow, ok);
       const float depth = sqrtf(x * x + y * y + z * z);
       ok = ok && depth > 0.0f;
       if (have && ok) atomicMin(&img[pix], __float_as_uint(depth));
@@ -286,13 +309,13 @@ extern "C" int rpcc_project_batch(const float* points, int stride, const int64_t
   cudaStream_t st = as_stream(stream);
   RPCC_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int32_t) * 4 * (size_t)B, st));
   const int grid = B < sm_count() ? B : sm_count();
-  // margins of fast_pixel(): 2.5x the worst-case distance between the fast and the reference
+  // margins of fast_pixel(): 4x the worst-case distance between the fast and the reference
   // coordinate.  col: 3 ulp of an angle in [4,8) (4.77e-7 each) scaled to columns + 4 ulp of W;
   // row: 3 ulp of an angle in [1,2) (1.19e-7 each) scaled to rows + 4 ulp of H.
   const float vres = (vmax - vmin) / (float)(H - 1);
   const float ulp_w = ldexpf(1.0f, ilogbf((float)(W > 1 ? W : 2)) - 23), ulp_h = ldexpf(1.0f, ilogbf((float)H) - 23);
-  float mcol = 2.5f * (3.0f * 4.77e-7f * (float)W / fabsf(hfov) + 4.0f * ulp_w);
-  float mrow = 2.5f * (3.0f * 1.2e-7f / fabsf(vres) + 4.0f * ulp_h);
+  float mcol = 4.0f * (3.0f * 4.77e-7f * (float)W / fabsf(hfov) + 4.0f * ulp_w);
+  float mrow = 4.0f * (3.0f * 1.2e-7f / fabsf(vres) + 4.0f * ulp_h);
   if (!(mcol < 0.25f)) mcol = 1.0f;   // margins this large disable the fast path (everything goes exact)
   if (!(mrow < 0.25f)) mrow = 1.0f;
   if (stride == 4)
