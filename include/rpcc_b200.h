@@ -103,9 +103,12 @@ RPCC_API size_t rpcc_book_bytes(int B, int H, int W, int K);
 
 /* a4 (second half, utils/segment_utils.py:143-148,168-169) + a6 accumulation
  * (cpp_modules.cpp:471-518): per-pixel argmin over {ground, m centres} with torch's float32
- * arithmetic.  labels [B][HW] u8.  Fills `book` (K = m + 2) for the next two stages. */
+ * arithmetic.  labels [B][HW] u8.  Fills `book` (K = m + 2) for the next two stages.
+ * workspace: rpcc_assign_workspace_bytes(B, m) bytes of device memory. */
 RPCC_API int rpcc_assign_labels_batch(const float* range, const float* lut, const float* ground, const float* centers,
-                             int B, int H, int W, int m, uint8_t* labels, void* book, void* stream);
+                             int B, int H, int W, int m, uint8_t* labels, void* book, void* workspace, void* stream);
+/* device scratch for the above (centres sorted by norm, per frame) */
+RPCC_API size_t rpcc_assign_workspace_bytes(int B, int m);
 
 /* Same bookkeeping for callers that bring their own labels (the standalone quantize ops). */
 RPCC_API int rpcc_label_stats_batch(const float* range, const uint8_t* labels, int B, int H, int W, int K,

@@ -25,47 +25,57 @@ namespace rpcc {
 
 constexpr int kTile = RPCC_TILE;  // 1024 threads, one pixel each
 
-// Centres are kept sorted by their distance to the sensor; a pixel at range r only has to look at the
-// centres whose norm lies within its current best distance of r (| |p| - |c| | <= |p - c|), walking
-// outwards from r and stopping as soon as the nearer side of the window is out of reach.  The skip
-// test carries a slack that covers every float rounding involved (|p| vs r, the computed norms, the
-// reference's own distance arithmetic), so a skipped centre can neither beat nor tie the current
-// best; the evaluated ones use the reference arithmetic verbatim, with torch.max's first-index rule.
+// Centres are kept sorted by their distance to the sensor (sort_centers_kernel, once per frame); a
+// pixel at range r only has to look at the centres whose norm lies within its current best distance
+// of r (| |p| - |c| | <= |p - c|), walking outwards from r and stopping as soon as the nearer side of
+// the window is out of reach.  The skip test carries a slack that covers every float rounding involved
+// (|p| vs r, the computed norms, the reference's own distance arithmetic), so a skipped centre can
+// neither beat nor tie the current best; the evaluated ones use the reference arithmetic verbatim,
+// with torch.max's first-index rule.
+__global__ void __launch_bounds__(128)
+sort_centers_kernel(const float* __restrict__ centers, int m, float4* __restrict__ sorted_xyzi, float* __restrict__ sorted_norm) {
+  extern __shared__ float s_n[];
+  const int f = blockIdx.x;
+  for (int c = threadIdx.x; c < m; c += blockDim.x) {
+    const float* cp = centers + ((size_t)f * m + c) * 3;
+    s_n[c] = sqrtf(cp[0] * cp[0] + cp[1] * cp[1] + cp[2] * cp[2]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < m; c += blockDim.x) {
+    const float cn = s_n[c];
+    int rank = 0;  // position in (norm, index) order
+    for (int q = 0; q < m; ++q) {
+      const float o = s_n[q];
+      rank += (o < cn || (o == cn && q < c)) ? 1 : 0;
+    }
+    const float* cp = centers + ((size_t)f * m + c) * 3;
+    sorted_xyzi[(size_t)f * m + rank] = make_float4(cp[0], cp[1], cp[2], __int_as_float(c + 1));
+    sorted_norm[(size_t)f * m + rank] = cn;
+  }
+}
+
 __global__ void __launch_bounds__(kTile, 2)
 assign_labels_kernel(const float* __restrict__ range, const float* __restrict__ lut, const float* __restrict__ ground,
-                     const float* __restrict__ centers, int HW, int W, int m, int T, uint8_t* __restrict__ labels,
-                     Book bk) {
+                     const float4* __restrict__ sorted_xyzi, const float* __restrict__ sorted_norm, int HW, int W, int m,
+                     int T, uint8_t* __restrict__ labels, Book bk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int K = m + 2;
-  float4* s_c = reinterpret_cast<float4*>(smem_raw);                               // [m] centres sorted by norm: x,y,z,norm
+  float4* s_c = reinterpret_cast<float4*>(smem_raw);                               // [m] x, y, z, bits(centre index + 1)
   unsigned long long* s_sum = reinterpret_cast<unsigned long long*>(s_c + m);     // [K]
   unsigned* s_cnt = reinterpret_cast<unsigned*>(s_sum + K);                       // [K]
   unsigned* s_flag = s_cnt + K;
   unsigned* s_ccnt = s_flag + 1;
   unsigned* s_last = s_ccnt + 1;                                                  // [32]
-  float* s_norm = reinterpret_cast<float*>(s_last + 32);                          // [m] unsorted norms (scratch)
-  unsigned char* s_id = reinterpret_cast<unsigned char*>(s_norm + m);             // [m] original index of sorted slot
+  float* s_norm = reinterpret_cast<float*>(s_last + 32);                          // [m + 2]: -inf, norms ascending, +inf
 
   const int f = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
-  float cx = 0.f, cy = 0.f, cz = 0.f, cn = 0.f;
   if (tid < m) {
-    const float* cp = centers + ((size_t)f * m + tid) * 3;
-    cx = cp[0]; cy = cp[1]; cz = cp[2];
-    cn = sqrtf(cx * cx + cy * cy + cz * cz);
-    s_norm[tid] = cn;
+    s_c[tid] = sorted_xyzi[(size_t)f * m + tid];
+    s_norm[tid + 1] = sorted_norm[(size_t)f * m + tid];
   }
+  if (tid == 0) { s_norm[0] = __int_as_float(0xff800000); s_norm[m + 1] = __int_as_float(0x7f800000); }
   for (int l = tid; l < K; l += kTile) { s_cnt[l] = 0; s_sum[l] = 0; }
   if (tid == 0) { *s_flag = 0; *s_ccnt = 0; }
-  __syncthreads();
-  if (tid < m) {
-    int rank = 0;  // counting sort position: (norm, index) ascending
-    for (int q = 0; q < m; ++q) {
-      const float o = s_norm[q];
-      rank += (o < cn || (o == cn && q < tid)) ? 1 : 0;
-    }
-    s_c[rank] = make_float4(cx, cy, cz, cn);
-    s_id[rank] = (unsigned char)tid;
-  }
   __syncthreads();
 
   const int p = tile * kTile + tid;
@@ -81,31 +91,30 @@ assign_labels_kernel(const float* __restrict__ range, const float* __restrict__ 
       const float rplane = (-g3) / torch_sum3(g0 * t0, g1 * t1, g2 * t2);
       float best = fabsf(r - rplane);
       int bi = 0;
-      // lower bound: first sorted slot whose norm is >= r
-      int lo = 0, n = m;
+      // lower bound in the padded norm array: first slot (1-based) whose norm is >= r
+      int lo = 1, n = m;
       while (n > 0) {
         const int half = n >> 1;
-        const bool right = s_c[lo + half].w < r;
+        const bool right = s_norm[lo + half] < r;
         lo = right ? lo + half + 1 : lo;
         n = right ? n - half - 1 : half;
       }
-      int hi = lo;      // next slot above r
-      lo = lo - 1;      // next slot below r
+      int hi = lo;      // next slot above r (m + 1 = exhausted, norm +inf)
+      lo = lo - 1;      // next slot below r (0 = exhausted, norm -inf)
+      float dlo = r - s_norm[lo], dhi = s_norm[hi] - r;
+      const float slack = 2e-6f * (r + r), kscale = 0.99999f;
       while (true) {
-        const float dlo = lo >= 0 ? r - s_c[lo >= 0 ? lo : 0].w : __int_as_float(0x7f800000);
-        const float dhi = hi < m ? s_c[hi < m ? hi : 0].w - r : __int_as_float(0x7f800000);
         const bool take_lo = dlo <= dhi;
         const float dn = take_lo ? dlo : dhi;
+        // | |p| - |c| | with every rounding on the safe side (|c| <= r + dn); +inf ends the walk; a NaN best
+        // (degenerate ground plane) never skips
+        if (!(dn < 3.0e38f) || (dn - slack - 2e-6f * dn) * kscale > best) break;
         const int slot = take_lo ? lo : hi;
-        if (slot < 0 || slot >= m) break;                      // both sides exhausted
-        const float4 cc = s_c[slot];
-        // | |p| - |c| | with every rounding on the safe side; NaN best (degenerate ground plane) never skips
-        if ((dn - 2e-6f * (r + cc.w)) * 0.99999f > best) break;
-        lo = take_lo ? lo - 1 : lo;
-        hi = take_lo ? hi : hi + 1;
+        const float4 cc = s_c[slot - 1];
+        if (take_lo) { --lo; dlo = r - s_norm[lo]; } else { ++hi; dhi = s_norm[hi] - r; }
         const float dx = x - cc.x, dy = y - cc.y, dz = z - cc.z;
         const float v = sqrtf(torch_sum3(dx * dx, dy * dy, dz * dz));
-        const int ci = (int)s_id[slot] + 1;
+        const int ci = __float_as_int(cc.w);
         if (v < best || (v == best && ci < bi)) { best = v; bi = ci; }
       }
       label = bi > 0 ? bi + 1 : 0;
@@ -162,9 +171,12 @@ extern "C" size_t rpcc_book_bytes(int B, int H, int W, int K) {
   return book_bytes(B, T, K);
 }
 
+extern "C" size_t rpcc_assign_workspace_bytes(int B, int m) { return (size_t)B * m * 20 + 64; }
+
 extern "C" int rpcc_assign_labels_batch(const float* range, const float* lut, const float* ground, const float* centers,
-                                        int B, int H, int W, int m, uint8_t* labels, void* book, void* stream) {
-  RPCC_REQUIRE(range && lut && ground && centers && labels && book, "null pointer");
+                                        int B, int H, int W, int m, uint8_t* labels, void* book, void* workspace,
+                                        void* stream) {
+  RPCC_REQUIRE(range && lut && ground && centers && labels && book && workspace, "null pointer");
   RPCC_REQUIRE(m >= 1 && m + 2 <= RPCC_MAX_LABELS, "cluster_num must be in [1, 254]");
   RPCC_REQUIRE(B <= 65535, "at most 65535 frames per launch");
   if (B == 0) return RPCC_OK;
@@ -173,9 +185,13 @@ extern "C" int rpcc_assign_labels_batch(const float* range, const float* lut, co
   const Book bk = make_book(book, B, T, K);
   int rc = zero_book(bk, B, K, st);
   if (rc != RPCC_OK) return rc;
+  float4* sorted_xyzi = reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(workspace) + 15) & ~(uintptr_t)15);
+  float* sorted_norm = reinterpret_cast<float*>(sorted_xyzi + (size_t)B * m);
+  sort_centers_kernel<<<B, 128, sizeof(float) * m, st>>>(centers, m, sorted_xyzi, sorted_norm);
+  RPCC_LAUNCH_CHECK("sort_centers_kernel");
   const size_t smem = sizeof(float4) * m + (sizeof(unsigned long long) + sizeof(unsigned)) * K + sizeof(unsigned) * 34 +
-                      sizeof(float) * m + m + 16;
-  assign_labels_kernel<<<dim3(T, B), kTile, smem, st>>>(range, lut, ground, centers, HW, W, m, T, labels, bk);
+                      sizeof(float) * (m + 2) + 16;
+  assign_labels_kernel<<<dim3(T, B), kTile, smem, st>>>(range, lut, ground, sorted_xyzi, sorted_norm, HW, W, m, T, labels, bk);
   RPCC_LAUNCH_CHECK("assign_labels_kernel");
   return RPCC_OK;
 }

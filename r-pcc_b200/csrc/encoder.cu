@@ -41,6 +41,7 @@ struct Slot {
   uint8_t* salience = nullptr;
   float* step_per_label = nullptr;
   uint32_t* kp_cnt = nullptr;
+  void* assign_ws = nullptr;    // centres sorted by norm
   // pinned host mirrors for the small per-chunk tables
   rpcc_frame_result* h_results = nullptr;
   int64_t* h_offsets = nullptr;
@@ -110,6 +111,7 @@ int alloc_slot(rpcc_encoder* e, Slot& s) {
   void* bk = nullptr;
   RPCC_CUDA(cudaMalloc(&bk, book_bytes((int)B, e->T, (int)K)));
   s.book = bk;
+  RPCC_CUDA(cudaMalloc(&s.assign_ws, rpcc_assign_workspace_bytes((int)B, (int)m)));
   RPCC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&s.h_results), sizeof(rpcc_frame_result) * B));
   RPCC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&s.h_offsets), sizeof(int64_t) * (B + 1)));
   return RPCC_OK;
@@ -118,7 +120,7 @@ int alloc_slot(rpcc_encoder* e, Slot& s) {
 void free_slot(Slot& s) {
   void* ptrs[] = {s.points, s.offsets, s.range, s.scratch, s.ground, s.center_idx, s.centers, s.labels, s.book, s.model,
                   s.results, s.sym_base, s.seq_base, s.symbols, s.seq, s.contour, s.key_points, s.salience,
-                  s.step_per_label, s.kp_cnt};
+                  s.step_per_label, s.kp_cnt, s.assign_ws};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s.ev) {
     for (int i = 0; i < kEvRing * (kStages + 1); ++i) if (s.ev[i]) cudaEventDestroy(s.ev[i]);
@@ -159,7 +161,7 @@ int run_chain(rpcc_encoder* e, Slot& s, const float* points, int stride, const i
   if ((rc = rpcc_segment_fps_batch(s.range, e->lut, s.ground, B, c.H, c.W, c.cluster_num, c.ground_threshold,
                                    s.center_idx, s.centers, st))) return rc;
   MARK(3);
-  if ((rc = rpcc_assign_labels_batch(s.range, e->lut, s.ground, s.centers, B, c.H, c.W, c.cluster_num, s.labels, s.book, st))) return rc;
+  if ((rc = rpcc_assign_labels_batch(s.range, e->lut, s.ground, s.centers, B, c.H, c.W, c.cluster_num, s.labels, s.book, s.assign_ws, st))) return rc;
   MARK(4);
   if (c.nonuniform) {
     if ((rc = rpcc_keypoints_salience_batch(s.range, s.labels, s.book, B, c.H, c.W, e->K, c.feature_region, c.segments,
