@@ -125,6 +125,26 @@ def test_project_rounding_boundary_stress(T, R):
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (lidar, int((got != want).sum()))
 
 
+def test_project_random_cloud_stress(T, R):
+    """2M random points per lidar table: directions well outside the vertical field of view (row clamp,
+    the exact-path elevations), all ranges from millimetres to kilometres, many collisions per pixel."""
+    g = np.random.default_rng(5)
+    for lidar in LIDARS:
+        cfg = R.LidarConfig(lidar)
+        H, W, hf, vmax, vmin = oracle.lidar_params(lidar)
+        n = 2000000
+        az = g.uniform(-np.pi, np.pi, n)
+        el = np.where(g.random(n) < 0.8, g.uniform(vmin - 0.05, vmax + 0.05, n), g.uniform(-1.55, 1.55, n))
+        r = 10.0 ** g.uniform(-3, 3.5, n)
+        pts = np.stack([r * np.cos(el) * np.cos(az), r * np.cos(el) * np.sin(az), r * np.sin(el), g.random(n)], -1).astype(np.float32)
+        off = np.array([0, n // 3, n // 3, n], np.int64)   # three frames, the middle one empty
+        rng = R.device_mod.project_batch(T.from_numpy(pts).cuda(), T.from_numpy(off).cuda(), cfg)
+        got = rng.cpu().numpy()
+        for b in range(3):
+            want = oracle.project(pts[off[b]:off[b + 1]], H, W, hf, vmax, vmin)
+            assert np.array_equal(got[b].view(np.uint32), want.view(np.uint32)), (lidar, b, int((got[b] != want).sum()))
+
+
 def test_project_many_synthetic_frames(T, R):
     pts, off, _ = _frames(R, "Velodyne64E", range(100, 140))
     cfg, rng = _project_dev(T, R, pts, off, "Velodyne64E")
