@@ -7,7 +7,7 @@ import os
 import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "librpcc_b200.so")
+LIB_PATH = os.environ.get("RPCC_B200_LIB") or os.path.join(_PKG, "lib", "librpcc_b200.so")  # env: A/B builds
 _lib = None
 
 

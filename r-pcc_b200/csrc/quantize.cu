@@ -17,9 +17,16 @@
 
 namespace rpcc {
 
-constexpr int kQThreads = 256;              // 8 warps per 1024-pixel tile
-constexpr int kQPer = RPCC_TILE / kQThreads; // 4 pixels per thread, strided by 256 (coalesced)
-constexpr int kQChunks = RPCC_TILE / 32;     // 32 warp-sized chunks per tile, chunk = j*8 + warp
+constexpr int kQWarps = 8;                  // one 1024-pixel tile per warp, 8 tiles per CTA
+constexpr int kQThreads = kQWarps * 32;
+#ifndef RPCC_QSLICES
+#define RPCC_QSLICES 4
+#endif
+#ifndef RPCC_QOCC
+#define RPCC_QOCC 6
+#endif
+constexpr int kQSlices = RPCC_QSLICES;      // 32-pixel slices per step: that many independent loads in flight per lane
+constexpr int kQSteps = RPCC_TILE / (32 * kQSlices);
 
 __device__ __forceinline__ float predict_range(const float4 m, const float* __restrict__ lut3) {
   // cpp_modules.cpp:271-279
@@ -27,8 +34,13 @@ __device__ __forceinline__ float predict_range(const float4 m, const float* __re
   return -m.w / (m.x * lut3[0] + m.y * lut3[1] + m.z * lut3[2]);
 }
 
+// One warp walks one tile in raster order, 32 consecutive pixels (a slice) at a time, and needs no
+// block-level synchronisation: its private counters s_cnt[warp][label] start at tile_off (the position,
+// in the frame's label-major symbol stream, of the tile's first symbol of that label) and advance as the
+// slices go by, so that the stable rank of a pixel is counter + (same-label lanes below it) -- one
+// match_any per slice.  Contour bits come from one ballot per slice, MSB-first bytes from brev.
 template <typename SymT>
-__global__ void __launch_bounds__(kQThreads, 4)
+__global__ void __launch_bounds__(kQThreads, RPCC_QOCC)
 quantize_pack_kernel(const float* __restrict__ range, const uint8_t* __restrict__ labels, const float* __restrict__ model,
                      const float* __restrict__ lut, Book bk, const float* __restrict__ step_per_label, float step,
                      int HW, int W, int K, int T, SymT* __restrict__ symbols, size_t sym_stride,
@@ -36,110 +48,113 @@ quantize_pack_kernel(const float* __restrict__ range, const uint8_t* __restrict_
                      const unsigned long long* __restrict__ sym_base, const unsigned long long* __restrict__ seq_base) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* s_model = reinterpret_cast<float4*>(smem_raw);            // [K]
-  float* s_step = reinterpret_cast<float*>(s_model + K);            // [K]
-  unsigned* s_tb = reinterpret_cast<unsigned*>(s_step + K);         // [K] first symbol of (tile,label) in the frame stream
-  unsigned* s_last = s_tb + K;                                      // [32] last label of each chunk
-  unsigned* s_wc = s_last + kQChunks;                               // [32] contour bits per chunk
-  unsigned* s_ccnt = s_wc + kQChunks;                               // [32*Kp/2] per-chunk label counts -> offsets (u16 pairs)
-  const int Kp = (K + 1) & ~1;                                      // row pitch in u16, even so rows are u32-aligned
-  uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_ccnt);
-  uint16_t* s_tcnt = s_cnt + kQChunks * Kp;                         // [K] pixels of each label in this tile
+  float2* s_step = reinterpret_cast<float2*>(s_model + K);          // [K] step, 1 / step
+  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_step + K);        // [kQWarps][K] next symbol position per label
 
-  const int f = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+  const int f = blockIdx.y, tid = threadIdx.x;
   const unsigned lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x * kQWarps + (int)warp;
   for (int l = tid; l < K; l += kQThreads) {
     s_model[l] = reinterpret_cast<const float4*>(model)[(size_t)f * K + l];
-    s_step[l] = step_per_label ? step_per_label[(size_t)f * K + l] : step;
-    s_tb[l] = bk.tile_off[((size_t)f * T + tile) * K + l];
-    s_tcnt[l] = bk.tile_hist[((size_t)f * T + tile) * K + l];
+    const float st = step_per_label ? step_per_label[(size_t)f * K + l] : step;
+    s_step[l] = make_float2(st, 1.0f / st);
   }
-  for (int i = tid; i < kQChunks * Kp / 2; i += kQThreads) s_ccnt[i] = 0;
+  unsigned* cnt = s_cnt + warp * K;
+  if (tile < T)
+    for (int l = lane; l < K; l += 32) cnt[l] = bk.tile_off[((size_t)f * T + tile) * K + l];
   __syncthreads();
+  if (tile >= T) return;
 
-  int label[kQPer], q[kQPer];
-  unsigned rank[kQPer];
   const size_t fbase = (size_t)f * HW;
+  const float* rg = range + fbase;
+  const uint8_t* lb = labels + fbase;
+  SymT* sym = symbols + (sym_base ? (size_t)sym_base[f] : (size_t)f * sym_stride);
+  uint16_t* sq = seq + (seq_base ? (size_t)seq_base[f] : (size_t)f * seq_stride) + bk.tile_coff[(size_t)f * T + tile];
+  uint8_t* cbits = contour_bits + (size_t)f * cbytes;
+  const int p_tile = tile * RPCC_TILE;
+  // label left of the tile's first pixel (-1: none, the pixel starts a run anyway)
+  int carry = (p_tile > 0 && p_tile < HW) ? (int)lb[p_tile - 1] : -1;
+  int next_row = ((p_tile + W - 1) / W) * W;     // next pixel that starts an image row (cpp_modules.cpp:537)
+  unsigned nseq = 0;                             // idx_sequence entries emitted by this tile so far
+
+#pragma unroll 1
+  for (int s = 0; s < kQSteps; ++s) {
+    const int p_step = p_tile + s * (32 * kQSlices);
+    if (p_step >= HW) break;
+    float r[kQSlices];
+    int lab[kQSlices];
 #pragma unroll
-  for (int j = 0; j < kQPer; ++j) {
-    const int p = tile * RPCC_TILE + j * kQThreads + tid;
-    label[j] = 1;
-    q[j] = 0;
-    if (p < HW) {
-      int l = labels[fbase + p];
+    for (int j = 0; j < kQSlices; ++j) {
+      const int p = p_step + j * 32 + (int)lane;
+      const bool inb = p < HW;
+      r[j] = inb ? ld_stream_f(rg + p) : 0.f;
+      lab[j] = inb ? (int)__ldg(lb + p) : 1;
+    }
+    unsigned words[kQSlices];
+#pragma unroll
+    for (int j = 0; j < kQSlices; ++j) {
+      const int p0 = p_step + j * 32, p = p0 + (int)lane;
+      const bool inb = p < HW;
+      int l = lab[j];
       if (l >= K) l = 1;  // flagged by label_stats; never emitted
-      const float r = range[fbase + p];
-      const float pred = predict_range(s_model[l], lut + (size_t)p * 3);
-      const float res = r - pred;
-      q[j] = (int)roundf(res / s_step[l]);
-      label[j] = l;
+      // ---- symbol (cpp_modules.cpp:264-281, tools/compress.py:106, cpp_modules.cpp:311-331)
+      int q = 0;
+      if (l != 1) {
+        const float pred = predict_range(s_model[l], lut + (size_t)p * 3);
+        const float res = r[j] - pred;
+        // q = (int)roundf(res / step) (cpp_modules.cpp:318): the reciprocal product is within 1.8e-7 |t| of the
+        // IEEE quotient, so unless it lies within 1e-6 |t| of a rounding boundary (k + 0.5) both round to the
+        // same integer; the few that do (and NaN / huge values) take the division
+        const float2 st = s_step[l];
+        const float t = res * st.y, at = fabsf(t);
+        const float fl = floorf(at + 0.5f), d = (at + 0.5f) - fl;
+        if (fminf(d, 1.0f - d) > at * 1e-6f) q = t < 0.0f ? -(int)fl : (int)fl;
+        else q = (int)roundf(res / st.x);
+      }
+      // ---- stable position: private counter + rank among the slice's lanes with the same label
+      const unsigned grp = __match_any_sync(0xffffffffu, l);
+      const int leader = __ffs(grp) - 1;
+      unsigned base = 0;
+      if ((int)lane == leader) { base = cnt[l]; cnt[l] = base + __popc(grp); }
+      base = __shfl_sync(0xffffffffu, base, leader);
+      __syncwarp();
+      if (l != 1) sym[(int)(base + __popc(grp & lanemask_lt()))] = (SymT)q;  // int16: wraps like astype(np.int16)
+      // ---- contour bit (cpp_modules.cpp:534-545) and idx_sequence
+      int left = __shfl_up_sync(0xffffffffu, l, 1);
+      if (lane == 0) left = carry;
+      carry = __shfl_sync(0xffffffffu, l, 31);
+      bool rowstart = false;
+      if (W >= 32) {
+        if (next_row < p0 + 32) { rowstart = (p == next_row); next_row += W; }
+      } else {
+        rowstart = (p % W) == 0;
+      }
+      const unsigned cb = __ballot_sync(0xffffffffu, inb && (rowstart || l != left));
+      if ((cb >> lane) & 1u) sq[(int)(nseq + __popc(cb & lanemask_lt()))] = (uint16_t)l;
+      nseq += __popc(cb);
+      words[j] = __byte_perm(__brev(cb), 0, 0x0123);   // np.packbits: pixel p0+i -> byte i/8, bit 7-(i%8)
     }
-    const unsigned grp = __match_any_sync(0xffffffffu, label[j]);
-    rank[j] = __popc(grp & lanemask_lt());
-    const int c = j * (kQThreads / 32) + warp;
-    if (rank[j] == 0) s_cnt[c * Kp + label[j]] = (uint16_t)__popc(grp);
-    if (lane == 31) s_last[c] = (unsigned)label[j];
-  }
-  __syncthreads();
-
-  // contour bits (cpp_modules.cpp:534-545), MSB-first packing (np.packbits): pixel p0+i -> byte i/8, bit 7-(i%8)
-  unsigned cb[kQPer];
+    // ---- contour bytes of the step: 4 bytes per slice
+    const int byte0 = p_step >> 3;
+    if ((cbytes & 15) == 0 && byte0 + 4 * kQSlices <= cbytes) {        // every frame's bitmap is 16-byte aligned
+      if (lane == 0) {
+        uint4* dst = reinterpret_cast<uint4*>(cbits + byte0);
 #pragma unroll
-  for (int j = 0; j < kQPer; ++j) {
-    const int c = j * (kQThreads / 32) + warp;
-    const int p = tile * RPCC_TILE + j * kQThreads + tid;
-    const bool inb = p < HW;
-    int left = __shfl_up_sync(0xffffffffu, label[j], 1);
-    if (lane == 0) left = c > 0 ? (int)s_last[c - 1] : (p > 0 && inb ? (int)labels[fbase + p - 1] : -1);
-    const bool cbit = inb && ((p % W) == 0 || label[j] != left);
-    cb[j] = __ballot_sync(0xffffffffu, cbit);
-    if (lane == 0) s_wc[c] = __popc(cb[j]);
-    const unsigned word = __byte_perm(__brev(cb[j]), 0, 0x0123);
-    const int byte0 = (tile * RPCC_TILE + c * 32) >> 3;
-    uint8_t* dst = contour_bits + (size_t)f * cbytes + byte0;
-    if ((cbytes & 3) == 0 && byte0 + 4 <= cbytes) {
-      if (lane == 0) *reinterpret_cast<unsigned*>(dst) = word;
-    } else if (lane < 4 && byte0 + (int)lane < cbytes) {
-      dst[lane] = (uint8_t)(word >> (8 * lane));
-    }
-  }
-  // exclusive scan over the 32 chunks, only for the labels present in this tile; warp w owns l = w, w+8, ...
-  for (int l = warp; l < K; l += kQThreads / 32) {
-    if (s_tcnt[l] == 0) continue;
-    const unsigned cnt = s_cnt[lane * Kp + l];
-    unsigned incl = cnt;
+        for (int j = 0; j < kQSlices; j += 4) dst[j >> 2] = make_uint4(words[j], words[j + 1], words[j + 2], words[j + 3]);
+      }
+    } else if ((cbytes & 3) == 0 && byte0 + 4 * kQSlices <= cbytes) {
+      if (lane == 0) {
+        unsigned* dst = reinterpret_cast<unsigned*>(cbits + byte0);
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= (unsigned)o) incl += v;
-    }
-    s_cnt[lane * Kp + l] = (uint16_t)(incl - cnt);
-  }
-  __syncthreads();
-
-  const size_t sbase = sym_base ? (size_t)sym_base[f] : (size_t)f * sym_stride;
-  const size_t qbase = (seq_base ? (size_t)seq_base[f] : (size_t)f * seq_stride) + bk.tile_coff[(size_t)f * T + tile];
-  // contour bits before each chunk
-  unsigned cex;
-  {
-    const unsigned wc = s_wc[lane];
-    unsigned incl = wc;
+        for (int j = 0; j < kQSlices; ++j) dst[j] = words[j];
+      }
+    } else {
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= (unsigned)o) incl += v;
+      for (int j = 0; j < kQSlices; ++j) {
+        const int b = byte0 + 4 * j + (int)lane;
+        if (lane < 4 && b < cbytes) cbits[b] = (uint8_t)(words[j] >> (8 * lane));
+      }
     }
-    cex = incl - wc;
-  }
-#pragma unroll
-  for (int j = 0; j < kQPer; ++j) {
-    const int c = j * (kQThreads / 32) + warp;
-    const int p = tile * RPCC_TILE + j * kQThreads + tid;
-    if (p < HW && label[j] != 1) {
-      const unsigned pos = s_tb[label[j]] + s_cnt[c * Kp + label[j]] + rank[j];
-      symbols[sbase + pos] = (SymT)q[j];  // int16: wraps like astype(np.int16)
-    }
-    const unsigned before_chunk = __shfl_sync(0xffffffffu, cex, c);
-    if ((cb[j] >> lane) & 1u) seq[qbase + before_chunk + __popc(cb[j] & lanemask_lt())] = (uint16_t)label[j];
   }
 }
 
@@ -201,10 +216,8 @@ int quantize_pack_launch(const float* range, const uint8_t* labels, const float*
   if (B == 0) return RPCC_OK;
   const int HW = H * W, T = (HW + RPCC_TILE - 1) / RPCC_TILE;
   const Book bk = make_book(book, B, T, K);
-  const int Kp = (K + 1) & ~1;
-  const size_t smem = (sizeof(float4) + sizeof(float) + sizeof(unsigned)) * K + sizeof(unsigned) * 2 * kQChunks +
-                      sizeof(uint16_t) * ((size_t)kQChunks * Kp + K) + 16;
-  quantize_pack_kernel<SymT><<<dim3(T, B), kQThreads, smem, as_stream(stream)>>>(
+  const size_t smem = (sizeof(float4) + sizeof(float2)) * K + sizeof(unsigned) * (size_t)kQWarps * K;
+  quantize_pack_kernel<SymT><<<dim3((T + kQWarps - 1) / kQWarps, B), kQThreads, smem, as_stream(stream)>>>(
       range, labels, model, lut, bk, step_per_label, step, HW, W, K, T, symbols, sym_stride, contour_bits,
       (HW + 7) / 8, seq, seq_stride, reinterpret_cast<const unsigned long long*>(sym_base),
       reinterpret_cast<const unsigned long long*>(seq_base));
