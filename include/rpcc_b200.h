@@ -120,6 +120,23 @@ RPCC_API int rpcc_label_stats_batch(const float* range, const uint8_t* labels, i
 RPCC_API int rpcc_point_model_batch(const float* range, const uint8_t* labels, const float* ground, void* book,
                            int B, int H, int W, int K, float* model, rpcc_frame_result* results, void* stream);
 
+/* a6, model_method = 'plane' (utils/segment_utils.py:188-216): per-cluster RANSAC plane models.
+ * rpcc_label_order_batch lists the non-empty pixels of every frame in the label-major stable order of
+ * the symbol stream (order [B][order_stride] u32 flat pixel indices, first sym_count[b] valid); `book`
+ * must have been through rpcc_point_model_batch.  rpcc_plane_model_batch then overwrites, in
+ * model [B][K][4] (as rpcc_point_model_batch left it), the row of every cluster (label >= 2) that has
+ * at least min_pixels pixels (reference: 30) and whose plane -- least-squares planes of ransac_n (4)
+ * distinct points, `iterations` (10) hypotheses, inliers within dist_thr (0.1 m), refit on the inliers
+ * of the best -- passes plane_angle_validation (:84-93) at angle_threshold_deg (cfgs/compressor.yaml:30).
+ * Deterministic: keyed by (seed, first_frame + b, label).  open3d's segment_plane is not reproduced
+ * bit for bit (third-party, randomised; DESIGN.md "parity unpinned"). */
+RPCC_API int rpcc_label_order_batch(const uint8_t* labels, void* book, int B, int H, int W, int K, uint32_t* order,
+                           size_t order_stride, void* stream);
+RPCC_API int rpcc_plane_model_batch(const float* range, const float* lut, const uint32_t* order, size_t order_stride,
+                           void* book, int B, int H, int W, int K, int min_pixels, float dist_thr, int ransac_n,
+                           int iterations, float angle_threshold_deg, uint64_t seed, uint64_t first_frame,
+                           float* model, void* stream);
+
 /* a7+a8+a10. cpp_modules.cpp:248-285 intra_predict, :288-334 uniform_quantize (or :337-424 with
  * per-label steps), :521-558 extract_contour + np.packbits, fused.  step_per_label: NULL =>
  * uniform `step`; else [B][K] f32.  symbols: [B][sym_stride] i16 (first sym_count[b] valid),
@@ -221,6 +238,12 @@ RPCC_API int rpcc_op_segment(const float* range, const float* lut, const float* 
 RPCC_API int rpcc_op_chamfer(const float* xyz1, int n, const float* xyz2, int m, float* dist1, int32_t* idx1,
                     float* dist2, int32_t* idx2);
 
+/* PointCloudSegment.cluster_modeling (utils/segment_utils.py:172-217) for model_method 'plane' with host arrays:
+ * rows_out [cap_rows][4] f32 receives the rows of labels 1 .. K-1 (the array the reference returns: label 1 =
+ * [0,0,0,0], clusters = [a,b,c,d] or [0,0,0,mean]); *rows = K - 1. */
+RPCC_API int rpcc_op_plane_modeling(const float* range, const int32_t* seg, const float* lut, int H, int W,
+                           float angle_threshold_deg, uint64_t seed, float* rows_out, int cap_rows, int* rows);
+
 /* PCTransformer.range_image_to_point_cloud (dataset/transformer.py:94-101) with host arrays. */
 RPCC_API int rpcc_op_range_to_xyz(const float* range, const float* lut, int H, int W, float* xyz);
 /* The ground-plane fit of PointCloudSegment.segment (utils/segment_utils.py:101-108), host arrays. */
@@ -247,6 +270,8 @@ typedef struct rpcc_encoder_config {
   int max_batch;               /* frames per call */
   int64_t max_points;          /* total point rows per call */
   int device;                  /* CUDA device ordinal */
+  int model_method;            /* 0 = point (cfgs/compressor.yaml:29), 1 = plane */
+  float plane_angle_threshold; /* degrees, cfgs/compressor.yaml:30 */
 } rpcc_encoder_config;
 
 RPCC_API int rpcc_encoder_create(const rpcc_encoder_config* cfg, rpcc_encoder** out);
@@ -255,7 +280,9 @@ RPCC_API void rpcc_encoder_destroy(rpcc_encoder* enc);
  * frames; results of a call stay in its slot until the slot is used again. */
 RPCC_API int rpcc_encoder_slots(void);
 /* Device-resident inputs (bench `value`): points/offsets as rpcc_project_batch (device pointers),
- * B <= max_batch; ground_in NULL => fitted on device, else [B][4] f32 (device or pinned host).
+ * B <= max_batch; ground_in NULL => fitted on device, else [B][4] f32 (device or pinned host).  The
+ * deterministic RANSACs (ground plane, cluster planes) are keyed by the frame's index within the call, so
+ * the same call always produces the same bytes, however encode_host cuts it into chunks.
  * Enqueues the whole chain on the slot's stream; no synchronisation. */
 RPCC_API int rpcc_encoder_encode_device(rpcc_encoder* enc, int slot, const float* points, int stride,
                                const int64_t* offsets, int B, const float* ground_in);
@@ -274,14 +301,14 @@ RPCC_API int rpcc_encoder_sync(rpcc_encoder* enc);
 /* Per-stage device timing with CUDA events recorded on the slots' own streams between the stages of
  * every chain call (at most 256 calls per slot are kept).  rpcc_encoder_profile(enc, 1) starts a fresh
  * recording, (enc, 0) stops it.  rpcc_encoder_stage_times synchronises and returns the summed
- * milliseconds of the 7 stages {project, ground, fps, assign, keypoints, model, quantize}, the frames
+ * milliseconds of the 7 stages {project, ground, fps, assign, keypoints, model (+ plane models), quantize}, the frames
  * they cover and the number of chain calls. */
 RPCC_API int rpcc_encoder_profile(rpcc_encoder* enc, int enable);
 RPCC_API int rpcc_encoder_stage_times(rpcc_encoder* enc, double* ms_out, long long* frames_out, int* calls_out);
 RPCC_API void* rpcc_encoder_stream(rpcc_encoder* enc, int slot);
 /* Named device buffers of a slot (tests, chaining): "range","labels","model","symbols","seq","contour",
  * "results","center_idx","centers","ground","key_points","salience","step_per_label","sym_base",
- * "seq_base","lut","points","offsets".  NULL if unknown / not allocated. */
+ * "seq_base","lut","points","offsets","order".  NULL if unknown / not allocated. */
 RPCC_API void* rpcc_encoder_device_buffer(rpcc_encoder* enc, int slot, const char* name);
 
 #ifdef __cplusplus

@@ -274,15 +274,21 @@ def write_rpcc(sections, method="bzip2"):
 
 
 def compress_frame(points, lidar="Velodyne64E", ground_model=None, accuracy=0.02, nonuniform=False,
-                   cluster_num=100, assoc=0, fma_mode=0, cfg=None):
-    """tools/compress.py:44-133 for model_method='point' given the ground model; returns a dict of
-    every intermediate (the parity tests compare the CUDA path stage by stage)."""
+                   cluster_num=100, assoc=0, fma_mode=0, cfg=None, model_method="point", plane_seed=0,
+                   angle_threshold=75):
+    """tools/compress.py:44-133 given the ground model; returns a dict of every intermediate (the parity
+    tests compare the CUDA path stage by stage).  model_method='plane' uses oracle.plane (open3d stand-in)."""
     H, W, hfov, vmax, vmin = lidar_params(lidar)
     lut = transform_map(H, W, hfov, vmax, vmin)
     step = accuracy * 2
     ri = project(points, H, W, hfov, vmax, vmin)
     seg, cidx, centers = segment(ri, lut, ground_model, cluster_num, 0.1, assoc, fma_mode)
-    mp = model_param_point(ri, seg, ground_model)
+    if model_method == "plane":
+        from . import plane as _plane
+        cm = _plane.cluster_modeling_plane(lut, ri, seg, angle_threshold, plane_seed)
+        mp = np.concatenate((np.asarray(ground_model, np.float64).reshape(1, 4), cm), 0).astype(np.float32)
+    else:
+        mp = model_param_point(ri, seg, ground_model)
     pred = intra_predict(seg, mp, lut)
     res = ri - pred
     out = dict(range_image=ri, seg_idx=seg, center_idx=cidx, model_param=mp, pred=pred, lut=lut)

@@ -26,7 +26,8 @@ class _EncoderConfig(C.Structure):
                 ("nonuniform", C.c_int), ("level_num", C.c_int), ("level_kp_num", C.c_int * 8),
                 ("level_dacc", C.c_double * 8), ("ground_level", C.c_int), ("feature_region", C.c_int),
                 ("segments", C.c_int), ("sharp_num", C.c_int), ("less_sharp_num", C.c_int), ("flat_num", C.c_int),
-                ("max_batch", C.c_int), ("max_points", C.c_int64), ("device", C.c_int)]
+                ("max_batch", C.c_int), ("max_points", C.c_int64), ("device", C.c_int),
+                ("model_method", C.c_int), ("plane_angle_threshold", C.c_float)]
 
 
 RESULT_DTYPE = np.dtype([("sym_count", np.uint32), ("seq_count", np.uint32), ("model_rows", np.uint32),
@@ -38,19 +39,19 @@ def _pinned(shape, dtype):
 
 
 class BatchEncoder:
-    """project -> ground fit -> FPS -> labels -> (key points) -> point models -> quantise + pack for
+    """project -> ground fit -> FPS -> labels -> (key points) -> point (or plane) models -> quantise + pack for
     batches of frames.  `accuracy` is the yaml value (step = 2 * accuracy, tools/compress.py:46)."""
 
     def __init__(self, lidar="Velodyne64E", accuracy=None, nonuniform=None, compressor_cfg=None, max_batch=256,
-                 max_points=None, device=None, basic_compressor=None, workers=None):
+                 max_points=None, device=None, basic_compressor=None, workers=None, model_method=None):
         cfg = load_compressor_cfg(compressor_cfg) if not isinstance(compressor_cfg, dict) else compressor_cfg
         self.cfg = cfg
+        self.model_method = model_method or cfg["modeling_method"]
         self.lidar = lidar if isinstance(lidar, LidarConfig) else LidarConfig(lidar)
         if cfg["segment_method"] != "FPS":
             raise NotImplementedError("only FPS segmentation is on this path")
-        if cfg["modeling_method"] != "point":
-            raise NotImplementedError("the batched encoder covers point modelling; plane modelling goes through "
-                                      "PointCloudSegment.cluster_modeling")
+        if self.model_method not in ("point", "plane"):
+            raise ValueError("model_method must be 'point' or 'plane'")
         self.accuracy = cfg["accuracy"] if accuracy is None else accuracy
         self.step = self.accuracy * 2
         self.uniform = (cfg["compress_framework"] == "uniform") if nonuniform is None else (not nonuniform)
@@ -81,6 +82,8 @@ class BatchEncoder:
         c.max_batch = self.max_batch
         c.max_points = self.max_points
         c.device = self.device
+        c.model_method = 1 if self.model_method == "plane" else 0
+        c.plane_angle_threshold = float(cfg["plane_angle_threshold"])
         self._c = c
         self._h = C.c_void_p(0)
         check(_lib.lib().rpcc_encoder_create(C.byref(c), C.byref(self._h)))

@@ -42,6 +42,7 @@ struct Slot {
   float* step_per_label = nullptr;
   uint32_t* kp_cnt = nullptr;
   void* assign_ws = nullptr;    // centres sorted by norm
+  uint32_t* order = nullptr;    // plane modelling: pixels in label-major order [B][HW]
   // pinned host mirrors for the small per-chunk tables
   rpcc_frame_result* h_results = nullptr;
   int64_t* h_offsets = nullptr;
@@ -66,7 +67,6 @@ struct rpcc_encoder {
   float* lut = nullptr;
   Slot slot[kSlots];
   uint64_t ground_seed = 0x5EEDull;
-  uint64_t frames_seen = 0;
   bool profiling = false;
 };
 
@@ -107,6 +107,7 @@ int alloc_slot(rpcc_encoder* e, Slot& s) {
     A(step_per_label, B * K);
     A(kp_cnt, B * K);
   }
+  if (e->cfg.model_method == 1) { A(order, B * HW); }
 #undef A
   void* bk = nullptr;
   RPCC_CUDA(cudaMalloc(&bk, book_bytes((int)B, e->T, (int)K)));
@@ -120,7 +121,7 @@ int alloc_slot(rpcc_encoder* e, Slot& s) {
 void free_slot(Slot& s) {
   void* ptrs[] = {s.points, s.offsets, s.range, s.scratch, s.ground, s.center_idx, s.centers, s.labels, s.book, s.model,
                   s.results, s.sym_base, s.seq_base, s.symbols, s.seq, s.contour, s.key_points, s.salience,
-                  s.step_per_label, s.kp_cnt, s.assign_ws};
+                  s.step_per_label, s.kp_cnt, s.assign_ws, s.order};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s.ev) {
     for (int i = 0; i < kEvRing * (kStages + 1); ++i) if (s.ev[i]) cudaEventDestroy(s.ev[i]);
@@ -171,6 +172,11 @@ int run_chain(rpcc_encoder* e, Slot& s, const float* points, int stride, const i
   }
   MARK(5);
   if ((rc = rpcc_point_model_batch(s.range, s.labels, s.ground, s.book, B, c.H, c.W, e->K, s.model, s.results, st))) return rc;
+  if (c.model_method == 1) {
+    if ((rc = rpcc_label_order_batch(s.labels, s.book, B, c.H, c.W, e->K, s.order, (size_t)e->HW, st))) return rc;
+    if ((rc = rpcc_plane_model_batch(s.range, e->lut, s.order, (size_t)e->HW, s.book, B, c.H, c.W, e->K, 30, 0.1f, 4, 10,
+                                     c.plane_angle_threshold, e->ground_seed ^ 0x9E3779B97F4A7C15ull, first_frame, s.model, st))) return rc;
+  }
   if ((rc = rpcc_frame_offsets_batch(s.results, B, s.sym_base, s.seq_base, st))) return rc;
   MARK(6);
   if ((rc = rpcc_quantize_pack_batch(s.range, s.labels, s.model, e->lut, s.book, c.nonuniform ? s.step_per_label : nullptr,
@@ -192,6 +198,7 @@ extern "C" int rpcc_encoder_create(const rpcc_encoder_config* cfg, rpcc_encoder*
   RPCC_REQUIRE(cfg->max_points >= 1, "max_points must be positive");
   RPCC_REQUIRE(cfg->step > 0, "step must be positive");
   RPCC_REQUIRE(!cfg->nonuniform || (cfg->level_num >= 1 && cfg->level_num <= 8), "1..8 salience levels");
+  RPCC_REQUIRE(cfg->model_method == 0 || cfg->model_method == 1, "model_method must be 0 (point) or 1 (plane)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -285,9 +292,8 @@ extern "C" int rpcc_encoder_encode_device(rpcc_encoder* e, int slot, const float
   RPCC_REQUIRE(slot >= 0 && slot < kSlots, "bad slot");
   if (B > e->cfg.max_batch) { set_error("rpcc_encoder_encode_device: B=%d exceeds max_batch=%d", B, e->cfg.max_batch); return RPCC_ERR_CAPACITY; }
   RPCC_CUDA(cudaSetDevice(e->cfg.device));
-  const uint64_t first = e->frames_seen;
-  e->frames_seen += (uint64_t)B;
-  return run_chain(e, e->slot[slot], points, stride, offsets, B, ground_in, first);
+  // the deterministic RANSACs are keyed by the frame's index within the call: the same call gives the same bytes
+  return run_chain(e, e->slot[slot], points, stride, offsets, B, ground_in, 0);
 }
 
 extern "C" int rpcc_encoder_sync(rpcc_encoder* e) {
@@ -308,7 +314,7 @@ extern "C" void* rpcc_encoder_device_buffer(rpcc_encoder* e, int slot, const cha
       {"range", s.range}, {"labels", s.labels}, {"model", s.model}, {"symbols", s.symbols}, {"seq", s.seq},
       {"contour", s.contour}, {"results", s.results}, {"center_idx", s.center_idx}, {"centers", s.centers},
       {"ground", s.ground}, {"key_points", s.key_points}, {"salience", s.salience}, {"step_per_label", s.step_per_label},
-      {"sym_base", s.sym_base}, {"seq_base", s.seq_base}, {"lut", e->lut}, {"points", s.points}, {"offsets", s.offsets}};
+      {"sym_base", s.sym_base}, {"seq_base", s.seq_base}, {"lut", e->lut}, {"points", s.points}, {"offsets", s.offsets}, {"order", s.order}};
   for (auto& t : tab) if (strcmp(t.n, name) == 0) return t.p;
   return nullptr;
 }
@@ -372,7 +378,7 @@ extern "C" int rpcc_encoder_encode_host(rpcc_encoder* e, const float* points_hos
       RPCC_CUDA(cudaMemcpyAsync(s.ground, ground_host + (size_t)f0 * 4, sizeof(float) * 4 * nb, cudaMemcpyHostToDevice, s.stream));
       gin = s.ground;
     }
-    rc = run_chain(e, s, s.points, stride, s.offsets, nb, gin, e->frames_seen + (uint64_t)f0);
+    rc = run_chain(e, s, s.points, stride, s.offsets, nb, gin, (uint64_t)f0);   // keys: index within this call, not the chunking
     if (rc) break;
     RPCC_CUDA(cudaMemcpyAsync(s.h_results, s.results, sizeof(rpcc_frame_result) * nb, cudaMemcpyDeviceToHost, s.stream));
     RPCC_CUDA(cudaEventRecord(s.done, s.stream));
@@ -386,6 +392,5 @@ extern "C" int rpcc_encoder_encode_host(rpcc_encoder* e, const float* points_hos
     const int r2 = check_cuda(cudaStreamSynchronize(e->slot[i].stream), "stream sync");
     if (rc == RPCC_OK) rc = r2;
   }
-  e->frames_seen += (uint64_t)B;
   return rc;
 }

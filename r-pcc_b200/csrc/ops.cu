@@ -414,3 +414,20 @@ extern "C" int rpcc_op_dequantize(const int16_t* symbols, int64_t n, const int32
   if (consumed) *consumed = r.sym_count;
   return download(residual_out, d_rng.p, HW * sizeof(float));
 }
+
+extern "C" int rpcc_op_plane_modeling(const float* range, const int32_t* seg, const float* lut, int H, int W,
+                                      float angle_threshold_deg, uint64_t seed, float* rows_out, int cap_rows, int* rows) {
+  RPCC_REQUIRE(range && seg && lut && rows_out && rows, "null pointer");
+  const size_t HW = (size_t)H * W;
+  FrameBook fb;
+  TRY(fb.build(range, seg, H, W, true));
+  RPCC_REQUIRE(cap_rows >= fb.K - 1, "rows_out too small");
+  DevBuf d_lut, d_order;
+  TRY(upload(d_lut, lut, HW * 3 * sizeof(float)));
+  TRY(d_order.alloc(HW * sizeof(uint32_t)));
+  TRY(rpcc_label_order_batch(fb.labels.as<uint8_t>(), fb.book.p, 1, H, W, fb.K, d_order.as<uint32_t>(), HW, nullptr));
+  TRY(rpcc_plane_model_batch(fb.range.as<float>(), d_lut.as<float>(), d_order.as<uint32_t>(), HW, fb.book.p, 1, H, W, fb.K,
+                             30, 0.1f, 4, 10, angle_threshold_deg, seed, 0, fb.model.as<float>(), nullptr));
+  *rows = fb.K - 1;
+  return download(rows_out, fb.model.as<float>() + 4, sizeof(float) * 4 * (size_t)(fb.K - 1));
+}

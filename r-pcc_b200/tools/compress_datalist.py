@@ -44,8 +44,8 @@ def load_points(path):
 
 def compress(args):
     cfg, accuracy, segment_cfg, model_cfg, uniform, method = resolve(args)
-    if model_cfg["model_method"] != "point" or segment_cfg["segment_method"] != "FPS":
-        raise NotImplementedError("the batched driver covers FPS + point modelling")
+    if model_cfg["model_method"] not in ("point", "plane") or segment_cfg["segment_method"] != "FPS":
+        raise NotImplementedError("the batched driver covers FPS segmentation with point or plane modelling")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -59,9 +59,10 @@ def compress(args):
     cfg = dict(cfg)
     cfg["cluster_num"] = segment_cfg["cluster_num"]
     cfg["ground_threshold"] = segment_cfg["ground_vertical_threshold"]
+    cfg["plane_angle_threshold"] = model_cfg["angle_threshold"]
     enc = BatchEncoder(args.lidar, accuracy=accuracy / 2, nonuniform=not uniform, compressor_cfg=cfg,
                        max_batch=min(args.batch, max(len(mine), 1)), device=local, basic_compressor=method,
-                       workers=args.workers)
+                       workers=args.workers, model_method=model_cfg["model_method"])
     bc = BasicCompressor(method_name=method)
     metrics = np.zeros((len(mine), 3), np.float64)  # bytes, valid pixels, seconds (amortised)
     pool = futures.ThreadPoolExecutor(args.workers)

@@ -140,3 +140,36 @@ def test_fps_tie_rule_matches_tree_order():
     assert oracle.fps(pts, 3)[1] == 2048
     pts[2048] = 0.0            # class 0 exhausted: next is thread 512 (bit-reversed id 1)
     assert oracle.fps(pts, 3)[1] == 512
+
+
+def test_plane_oracle_restatement_properties():
+    """oracle.plane (the reference's plane branch with a seeded stand-in for open3d, PARITY UNPINNED):
+    the pieces that ARE pinned by the reference's own text -- the < 30 pixel rule, the angle test's
+    expression, the row layout -- and the codec's error bound through the full oracle pipeline."""
+    from oracle import plane as oplane
+    import rpcc_b200  # noqa: F401  (registers the package alias; synthetic frames are plain numpy)
+    from rpcc_b200 import synthetic
+    pts, g = synthetic.frame(7, "Velodyne64E")
+    out = oracle.compress_frame(pts, "Velodyne64E", g, accuracy=0.02, model_method="plane", plane_seed=3)
+    ri, seg, mp, lut = out["range_image"], out["seg_idx"], out["model_param"], out["lut"]
+    cnt = np.bincount(seg.ravel(), minlength=mp.shape[0])
+    is_plane = np.abs(mp[:, :3]).sum(1) > 0
+    assert is_plane[0] and not is_plane[1]
+    assert not is_plane[2:][cnt[2:] < 30].any()
+    assert is_plane[2:].sum() > 20
+    rec, _, seg2 = oracle.decompress_sections(out["sections"], "Velodyne64E", 0.02)
+    assert np.array_equal(seg2, seg)
+    assert float(np.abs(rec - ri)[ri > 0].max()) <= 0.02 + 1e-5
+    # angle test: a plane facing the sensor passes, a grazing one is rejected, a NaN-poisoned one is kept
+    idx = np.where(seg == int(np.argmax(cnt[2:]) + 2))
+    s = lut[idx].astype(np.float64).mean(0)
+    s /= np.linalg.norm(s)
+    assert oplane.plane_angle_validation(lut, np.array([s[0], s[1], s[2], -10.0]), idx, 75)
+    t = np.cross(s, [0, 0, 1.0])
+    t /= np.linalg.norm(t)
+    assert not oplane.plane_angle_validation(lut, np.array([t[0], t[1], t[2], -1.0]), idx, 75)
+    # least-squares plane of exact coplanar points
+    q = np.random.default_rng(0).normal(size=(50, 3))
+    q[:, 2] = 0.25 * q[:, 0] - 0.5 * q[:, 1] + 3.0
+    pl = oplane.get_plane_from_points(q)
+    assert np.abs(q @ pl[:3] + pl[3]).max() < 1e-9 and abs(np.linalg.norm(pl[:3]) - 1) < 1e-12
