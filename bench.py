@@ -32,7 +32,7 @@ HW = 64 * 2000
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=1184, help="frames per step per GPU (default 4 x 296)")
@@ -68,7 +68,7 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.02)
 
     def __enter__(self):
         self.t.start()
@@ -181,12 +181,25 @@ def reference_arm(a):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------- main arm
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else a library prints (NCCL banners, warnings)
+    was diverted to stderr at start-up."""
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    global _JSON_FD
     a = parse()
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         reference_arm(a)
         return
@@ -369,7 +382,7 @@ def main():
                        "stage_timing": "roofline.kernels: the same steps re-run on one stream slot with CUDA events between stages"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu_baseline}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -21,6 +21,9 @@
 //    in shared memory), builds the masked point cloud straight from range x LUT, keeps a single
 //    representative of the identical origin points (ground / empty pixels) per residue class,
 //    and exchanges the per-CTA winners through distributed shared memory once per round.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace rpcc {
@@ -350,6 +353,185 @@ static int launch_segment_fps(const float* range, const float* lut, const float*
   return RPCC_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// fused mask + FPS with exact bucket pruning: one CTA per frame, state in L2
+// ------------------------------------------------------------------------------------------------
+// Round j of FPS only lowers the running distance t[k] of points that are closer to the new centre
+// than to every earlier one -- a few per cent of the image.  Pixels are grouped into buckets of 32
+// consecutive pixels (neighbours on one beam); a bucket keeps its bounding box, its maximum t
+// and the tie key of the point holding it.  A bucket whose box is farther from the new centre than
+// sqrt(max t) cannot change (the test carries a 1e-5 relative slack, two orders of magnitude above
+// the rounding of either side), so a round touches only the buckets around the new centre and the
+// argmax comes from the per-bucket maxima.  Touched points are updated with the reference's own
+// arithmetic, and maxima / tie keys are exact, so the seed sequence is the reference's, bit for bit.
+// Per frame this replaces 99 passes over 128 000 points by one pass plus ~100 buckets per round:
+// a single CTA per frame suffices, no cross-SM exchange, 148+ frames in flight.
+//   state in global memory (L2-resident): t[HW] per CTA, bit 31 = "masked to the origin"
+//   state on chip: boxes in shared memory (6 floats per bucket), max t / tie key in registers.
+constexpr unsigned kNoTie = 0xFFFFFFFFu;
+
+__device__ __forceinline__ int ford(float f) { const int b = __float_as_int(f); return b ^ ((b >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float ordf(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+
+template <int THREADS, int Q, int MINB>   // Q buckets per lane: the warp owns buckets warp + NW * (q * 32 + lane)
+__global__ void __launch_bounds__(THREADS, MINB)
+segment_fps_pruned_kernel(const float* __restrict__ range, const float* __restrict__ lut, const float* __restrict__ ground,
+                          int B, int HW, int m, float thr, unsigned* __restrict__ temp_ws, int* __restrict__ center_idx,
+                          float* __restrict__ centers) {
+  constexpr int NW = THREADS / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NB = (HW + 31) >> 5;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s_box = reinterpret_cast<float*>(smem_raw);            // [6][Q][THREADS]: x0,y0,z0,x1,y1,z1 of bucket (q, tid)
+  __shared__ uint2 s_part[2][32];
+  unsigned* temp = temp_ws + (size_t)blockIdx.x * HW;
+  const float INF = __int_as_float(0x7f800000);
+
+  for (int f = blockIdx.x; f < B; f += gridDim.x) {
+    const float* rg = range + (size_t)f * HW;
+    const float g0 = ground[f * 4], g1 = ground[f * 4 + 1], g2 = ground[f * 4 + 2], g3 = ground[f * 4 + 3];
+    const float gnorm = sqrtf(torch_sum3(g0 * g0, g1 * g1, g2 * g2));
+    // seed 0 is flat index 0 (sampling_gpu.cu:44-46)
+    float x1, y1, z1;
+    masked_point(rg[0], lut, g0, g1, g2, g3, gnorm, thr, x1, y1, z1);
+    if (tid == 0) {
+      center_idx[(size_t)f * m] = 0;
+      float* c = centers + (size_t)f * m * 3;
+      c[0] = x1; c[1] = y1; c[2] = z1;
+    }
+    // ---- first pass = round 1 over every bucket: t = min(d, 1e10), boxes, maxima, tie keys
+    unsigned bmax[Q], btk[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      bmax[q] = 0u; btk[q] = kNoTie;
+      float mx0 = INF, my0 = INF, mz0 = INF, mx1 = -INF, my1 = -INF, mz1 = -INF;
+#pragma unroll 2
+      for (int t = 0; t < 32; ++t) {
+        const int b = warp + NW * (q * 32 + t);
+        if (b >= NB) break;                                   // warp-uniform
+        const int p = (b << 5) + lane;
+        const bool inb = p < HW;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (inb) masked_point(rg[p], lut + (size_t)p * 3, g0, g1, g2, g3, gnorm, thr, x, y, z);
+        const bool origin = (x == 0.f) && (y == 0.f) && (z == 0.f);
+        const float tv = fminf(fps_dist(x, y, z, x1, y1, z1), 1e10f);
+        if (inb) temp[p] = __float_as_uint(tv) | (origin ? 0x80000000u : 0u);
+        const unsigned nb = inb ? __float_as_uint(tv) : 0u;
+        const unsigned newmax = __reduce_max_sync(0xffffffffu, nb);
+        const unsigned tk = (inb && nb == newmax) ? ((__brev((unsigned)p) & 0xFFC00000u) | ((unsigned)p >> 10)) : kNoTie;
+        const unsigned ntk = __reduce_min_sync(0xffffffffu, tk);
+        // box over the points that can still change (t > 0)
+        const bool live = inb && tv > 0.f;
+        const int big = 0x7fffffff;
+        const float a0 = ordf(__reduce_min_sync(0xffffffffu, live ? ford(x) : big));
+        const float a1 = ordf(__reduce_min_sync(0xffffffffu, live ? ford(y) : big));
+        const float a2 = ordf(__reduce_min_sync(0xffffffffu, live ? ford(z) : big));
+        const float a3 = ordf(__reduce_max_sync(0xffffffffu, live ? ford(x) : -big));
+        const float a4 = ordf(__reduce_max_sync(0xffffffffu, live ? ford(y) : -big));
+        const float a5 = ordf(__reduce_max_sync(0xffffffffu, live ? ford(z) : -big));
+        if (lane == t) { bmax[q] = newmax; btk[q] = ntk; mx0 = a0; my0 = a1; mz0 = a2; mx1 = a3; my1 = a4; mz1 = a5; }
+      }
+      // an all-dead / missing bucket keeps (+big, -big): its lower bound is huge and its maximum 0
+      float* bx = s_box + q * THREADS + tid;
+      bx[0] = mx0; bx[Q * THREADS] = my0; bx[2 * Q * THREADS] = mz0;
+      bx[3 * Q * THREADS] = mx1; bx[4 * Q * THREADS] = my1; bx[5 * Q * THREADS] = mz1;
+    }
+    // (boxes are private to their owner thread: no synchronisation needed before they are read back)
+
+    for (int j = 1; j < m; ++j) {
+      // ---- winner of the previous round (in round 1: of the first pass)
+      {
+        unsigned d = 0u, tk = kNoTie;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          const bool better = bmax[q] > d || (bmax[q] == d && btk[q] < tk);
+          d = better ? bmax[q] : d; tk = better ? btk[q] : tk;
+        }
+        const unsigned dw = __reduce_max_sync(0xffffffffu, d);
+        const unsigned tw = __reduce_min_sync(0xffffffffu, d == dw ? tk : kNoTie);
+        if (lane == 0) s_part[j & 1][warp] = make_uint2(dw, tw);
+        __syncthreads();
+        const uint2 v = lane < NW ? s_part[j & 1][lane] : make_uint2(0u, kNoTie);
+        const unsigned dmax = __reduce_max_sync(0xffffffffu, v.x);
+        const unsigned tkmin = __reduce_min_sync(0xffffffffu, v.x == dmax ? v.y : kNoTie);
+        const int k = (int)(((tkmin & 0x3FFFFFu) << 10) | __brev(tkmin & 0xFFC00000u));
+        const bool org = (temp[k] >> 31) != 0u;
+        const float r = rg[k];
+        x1 = org ? 0.f : r * lut[(size_t)k * 3]; y1 = org ? 0.f : r * lut[(size_t)k * 3 + 1]; z1 = org ? 0.f : r * lut[(size_t)k * 3 + 2];
+        if (tid == 0) {
+          center_idx[(size_t)f * m + j] = k;
+          float* c = centers + ((size_t)f * m + j) * 3;
+          c[0] = x1; c[1] = y1; c[2] = z1;
+        }
+      }
+      if (j == m - 1) break;                                  // the last centre needs no update pass
+      // ---- which of my buckets can change?
+      unsigned act[Q];
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const float* bx = s_box + q * THREADS + tid;
+        const float ox = fmaxf(fmaxf(bx[0] - x1, x1 - bx[3 * Q * THREADS]), 0.f);
+        const float oy = fmaxf(fmaxf(bx[Q * THREADS] - y1, y1 - bx[4 * Q * THREADS]), 0.f);
+        const float oz = fmaxf(fmaxf(bx[2 * Q * THREADS] - z1, z1 - bx[5 * Q * THREADS]), 0.f);
+        const float lb = __fmaf_rn(oz, oz, __fmaf_rn(oy, oy, ox * ox));
+        act[q] = __ballot_sync(0xffffffffu, lb * 0.99999f < __uint_as_float(bmax[q]));
+      }
+      // ---- update them with the reference arithmetic
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        unsigned a = act[q];
+        while (a) {
+          const int t = __ffs(a) - 1;
+          a &= a - 1;
+          const int b = warp + NW * (q * 32 + t);
+          const int p = (b << 5) + lane;
+          const bool inb = p < HW;
+          unsigned nb = 0u;
+          if (inb) {
+            const unsigned tb = temp[p];
+            const float r = __ldg(rg + p);
+            const float lx = __ldg(lut + (size_t)p * 3), ly = __ldg(lut + (size_t)p * 3 + 1), lz = __ldg(lut + (size_t)p * 3 + 2);
+            const bool org = (tb >> 31) != 0u;
+            const float x = org ? 0.f : r * lx, y = org ? 0.f : r * ly, z = org ? 0.f : r * lz;
+            const float told = __uint_as_float(tb & 0x7fffffffu);
+            const float tn = fminf(fps_dist(x, y, z, x1, y1, z1), told);          // sampling_gpu.cu:64-66
+            nb = __float_as_uint(tn);
+            if (tn != told) temp[p] = nb | (tb & 0x80000000u);
+          }
+          const unsigned newmax = __reduce_max_sync(0xffffffffu, nb);
+          const unsigned tk = (inb && nb == newmax) ? ((__brev((unsigned)p) & 0xFFC00000u) | ((unsigned)p >> 10)) : kNoTie;
+          const unsigned ntk = __reduce_min_sync(0xffffffffu, tk);
+          if (lane == t) { bmax[q] = newmax; btk[q] = ntk; }
+        }
+      }
+    }
+    __syncthreads();   // the next frame's first pass rewrites temp[] and s_part
+  }
+}
+
+template <int THREADS, int Q, int MINB>
+static int launch_fps_pruned(const float* range, const float* lut, const float* ground, int B, int HW, int m, float thr,
+                             int* center_idx, float* centers, cudaStream_t st) {
+  auto kern = segment_fps_pruned_kernel<THREADS, Q, MINB>;
+  const size_t smem = sizeof(float) * 6 * Q * THREADS;
+  RPCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  RPCC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+  if (per_sm < 1) per_sm = 1;
+  int grid = per_sm * sm_count();
+  if (grid > B) grid = B;
+  // running distances of the frames in flight: stream-ordered scratch, no synchronisation
+  void* ws = nullptr;
+  RPCC_CUDA(cudaMallocAsync(&ws, sizeof(unsigned) * (size_t)grid * HW, st));
+  kern<<<grid, THREADS, smem, st>>>(range, lut, ground, B, HW, m, thr, static_cast<unsigned*>(ws), center_idx, centers);
+  const cudaError_t le = cudaGetLastError();
+  RPCC_CUDA(cudaFreeAsync(ws, st));
+  RPCC_CUDA(le);
+  count_launch();
+  return RPCC_OK;
+}
+
 }  // namespace rpcc
 
 using namespace rpcc;
@@ -372,6 +554,32 @@ extern "C" int rpcc_segment_fps_batch(const float* range, const float* lut, cons
   RPCC_REQUIRE(HW >= 1024, "range image must have at least 1024 pixels");
   RPCC_REQUIRE(m >= 1, "need at least one seed");
   if (B == 0) return RPCC_OK;
+  static const bool use_cluster = getenv("RPCC_FPS_IMPL") && !strcmp(getenv("RPCC_FPS_IMPL"), "cluster");
+  static const int fps_threads = getenv("RPCC_FPS_THREADS") ? atoi(getenv("RPCC_FPS_THREADS")) : 1024;
+  if (!use_cluster && m >= 2) {
+    cudaStream_t st = as_stream(stream);
+    const int NB = (HW + 31) / 32;
+    static const int minb = getenv("RPCC_FPS_MINB") ? atoi(getenv("RPCC_FPS_MINB")) : 1;
+#define RPCC_FPS_GO(T, Q, M) return launch_fps_pruned<T, Q, M>(range, lut, ground, B, HW, m, ground_thr, center_idx, centers, st)
+    if (fps_threads == 512) {
+      const int q = (NB + 511) / 512;
+      if (q <= 2) RPCC_FPS_GO(512, 2, 2);
+      if (q <= 4) RPCC_FPS_GO(512, 4, 2);
+      if (q <= 8) RPCC_FPS_GO(512, 8, 2);
+    } else if (minb == 2) {
+      const int q = (NB + 1023) / 1024;
+      if (q <= 1) RPCC_FPS_GO(1024, 1, 2);
+      if (q <= 2) RPCC_FPS_GO(1024, 2, 2);
+      if (q <= 4) RPCC_FPS_GO(1024, 4, 2);
+    } else {
+      const int q = (NB + 1023) / 1024;
+      if (q <= 1) RPCC_FPS_GO(1024, 1, 1);
+      if (q <= 2) RPCC_FPS_GO(1024, 2, 1);
+      if (q <= 4) RPCC_FPS_GO(1024, 4, 1);
+    }
+#undef RPCC_FPS_GO
+    // larger images fall through to the cluster kernel (which has its own capacity check)
+  }
   const int J = (HW + kFpsThreads - 1) / kFpsThreads;
   const int need = (J + kCl - 1) / kCl;  // slots per thread
   cudaStream_t st = as_stream(stream);
