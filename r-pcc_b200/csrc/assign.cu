@@ -29,100 +29,161 @@ constexpr int kMaxQ = 8;          // centres per lane in the bound pass: up to 2
 __device__ __forceinline__ int f2ord(float f) { const int b = __float_as_int(f); return b ^ ((b >> 31) & 0x7fffffff); }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
 
-// A warp holds 32 consecutive pixels of one image row: neighbours in space.  Instead of every lane testing
-// every centre, the warp first bounds, for each centre (4 centres per lane), the distance from ANY of
-// its pixels: LB = distance to the pixels' bounding box, UB = distance to the box's farthest corner.  A
-// centre whose LB exceeds the smallest UB (with a 1e-5 relative slack that covers every float rounding
-// involved) can neither win nor tie for any pixel of the warp; the survivors -- a handful -- are then
-// evaluated by all lanes with the reference arithmetic verbatim, in ascending centre index with a strict
-// '<', which is torch.max's first-index rule.
-__global__ void __launch_bounds__(kTile, 2)
+constexpr int kAsWarps = 8;        // one 1024-pixel tile per warp, 8 tiles of one frame per CTA
+
+// One warp walks one tile, 32 consecutive pixels (a slice) at a time -- neighbours on one beam -- and
+// needs no block-level synchronisation after the centres are staged.  Per slice the warp bounds every
+// centre against the slice's bounding sphere (centre o, radius R): a centre can be nearest to some
+// pixel of the slice only if |c - o| <= min_c' |c' - o| + 2R.  That test costs 6 flops per centre
+// (centres spread over the lanes) and leaves a handful of survivors, which all lanes then evaluate with
+// the reference arithmetic verbatim, in ascending centre index with a strict '<' (torch.max's
+// first-index rule).  The slack of 1e-5 relative on both sides of the test is two orders of magnitude
+// above the rounding of the quantities compared, so a culled centre can neither win nor tie.
+// Label statistics go to per-warp bins in shared memory (no atomics: one leader lane per label and
+// slice) and are flushed once per tile.
+__global__ void __launch_bounds__(kAsWarps * 32, 6)
 assign_labels_kernel(const float* __restrict__ range, const float* __restrict__ lut, const float* __restrict__ ground,
                      const float* __restrict__ centers, int HW, int W, int m, int T, uint8_t* __restrict__ labels, Book bk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int K = m + 2;
   const int mq = (m + 31) / 32;                                                    // centres per lane
   float4* s_c = reinterpret_cast<float4*>(smem_raw);                               // [mq * 32] x, y, z, -
-  unsigned long long* s_sum = reinterpret_cast<unsigned long long*>(s_c + mq * 32); // [K]
-  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_sum + K);                       // [K]
-  unsigned* s_flag = s_cnt + K;
-  unsigned* s_ccnt = s_flag + 1;
-  unsigned* s_last = s_ccnt + 1;                                                  // [32]
+  unsigned long long* s_sum = reinterpret_cast<unsigned long long*>(s_c + mq * 32); // [kAsWarps][K]
+  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_sum + kAsWarps * K);            // [kAsWarps][K]
 
-  const int f = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-  if (tid < mq * 32) {
-    // padding centres sit at +inf: their lower bound is +inf and they never survive
+  const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x * kAsWarps + warp;
+  for (int c = tid; c < mq * 32; c += kAsWarps * 32) {
+    // padding centres sit at +inf: they never survive
     const float inf = __int_as_float(0x7f800000);
-    const float* cp = centers + ((size_t)f * m + tid) * 3;
-    s_c[tid] = tid < m ? make_float4(cp[0], cp[1], cp[2], 0.f) : make_float4(inf, inf, inf, 0.f);
+    const float* cp = centers + ((size_t)f * m + c) * 3;
+    s_c[c] = c < m ? make_float4(cp[0], cp[1], cp[2], 0.f) : make_float4(inf, inf, inf, 0.f);
   }
-  for (int l = tid; l < K; l += kTile) { s_cnt[l] = 0; s_sum[l] = 0; }
-  if (tid == 0) { *s_flag = 0; *s_ccnt = 0; }
+  unsigned long long* sum = s_sum + warp * K;
+  unsigned* cnt = s_cnt + warp * K;
+  for (int l = lane; l < K; l += 32) { cnt[l] = 0; sum[l] = 0; }
   __syncthreads();
+  if (tile >= T) return;
 
-  const int p = tile * kTile + tid;
-  const bool inb = p < HW;
-  int label = 1;
-  float r = 0.f, x = 0.f, y = 0.f, z = 0.f, best = 0.f;
-  if (inb) {
-    r = range[(size_t)f * HW + p];
-    if (r != 0.0f) {
-      const float t0 = lut[(size_t)p * 3], t1 = lut[(size_t)p * 3 + 1], t2 = lut[(size_t)p * 3 + 2];
-      const float g0 = ground[f * 4], g1 = ground[f * 4 + 1], g2 = ground[f * 4 + 2], g3 = ground[f * 4 + 3];
-      x = r * t0; y = r * t1; z = r * t2;
-      const float rplane = (-g3) / torch_sum3(g0 * t0, g1 * t1, g2 * t2);
-      best = fabsf(r - rplane);                     // channel 0 (utils/segment_utils.py:143)
-    }
-  }
-  const bool valid = inb && r != 0.0f;
-  if (__any_sync(0xffffffffu, valid)) {
-    // bounding box of the warp's valid points
-    const int big = 0x7fffffff;
-    const float bx0 = ord2f(__reduce_min_sync(0xffffffffu, valid ? f2ord(x) : big));
-    const float by0 = ord2f(__reduce_min_sync(0xffffffffu, valid ? f2ord(y) : big));
-    const float bz0 = ord2f(__reduce_min_sync(0xffffffffu, valid ? f2ord(z) : big));
-    const float bx1 = ord2f(__reduce_max_sync(0xffffffffu, valid ? f2ord(x) : -big));
-    const float by1 = ord2f(__reduce_max_sync(0xffffffffu, valid ? f2ord(y) : -big));
-    const float bz1 = ord2f(__reduce_max_sync(0xffffffffu, valid ? f2ord(z) : -big));
-    // per-centre bounds (squared), centre q * 32 + lane for q < mq; fused arithmetic is fine here, the slack covers it
-    float lb[kMaxQ];
-    float ubmin = __int_as_float(0x7f800000);
-#pragma unroll
-    for (int q = 0; q < kMaxQ; ++q) {
-      lb[q] = __int_as_float(0x7f800000);
-      if (q < mq) {
-        const float4 c = s_c[q * 32 + lane];
-        const float ax = bx0 - c.x, cx = c.x - bx1, ay = by0 - c.y, cy = c.y - by1, az = bz0 - c.z, cz = c.z - bz1;
-        const float ox = fmaxf(fmaxf(ax, cx), 0.f), oy = fmaxf(fmaxf(ay, cy), 0.f), oz = fmaxf(fmaxf(az, cz), 0.f);
-        const float fx = fmaxf(fabsf(ax), fabsf(cx)), fy = fmaxf(fabsf(ay), fabsf(cy)), fz = fmaxf(fabsf(az), fabsf(cz));
-        lb[q] = __fmaf_rn(oz, oz, __fmaf_rn(oy, oy, ox * ox));
-        const float ub = __fmaf_rn(fz, fz, __fmaf_rn(fy, fy, fx * fx));
-        ubmin = fminf(ubmin, ub);                 // NaN centres drop out here and below (comparisons are false)
+  const float g0 = ground[f * 4], g1 = ground[f * 4 + 1], g2 = ground[f * 4 + 2], g3 = ground[f * 4 + 3];
+  const float* rg = range + (size_t)f * HW;
+  uint8_t* lb = labels + (size_t)f * HW;
+  const int p_tile = tile * RPCC_TILE;
+  int next_row = ((p_tile + W - 1) / W) * W;       // next pixel that starts an image row
+  int carry = -1;                                  // label left of the slice (none for the tile's first pixel)
+  unsigned ccnt = 0, flag = 0;
+
+#pragma unroll 1
+  for (int s = 0; s < RPCC_TILE / 32; ++s) {
+    const int p0 = p_tile + s * 32, p = p0 + lane;
+    if (p0 >= HW) break;
+    const bool inb = p < HW;
+    int label = 1;
+    float r = 0.f, x = 0.f, y = 0.f, z = 0.f, best = 0.f;
+    if (inb) {
+      r = ld_stream_f(rg + p);
+      if (r != 0.0f) {
+        const float* l3 = lut + 3 * p;
+        const float t0 = __ldg(l3), t1 = __ldg(l3 + 1), t2 = __ldg(l3 + 2);
+        x = r * t0; y = r * t1; z = r * t2;
+        const float rplane = (-g3) / torch_sum3(g0 * t0, g1 * t1, g2 * t2);
+        best = fabsf(r - rplane);                     // channel 0 (utils/segment_utils.py:143)
       }
     }
-    const float thr = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(ubmin))) * 1.00001f;
-    int bi = 0;
+    const bool valid = inb && r != 0.0f;
+    if (__any_sync(0xffffffffu, valid)) {
+      // bounding sphere of the slice's valid points: box centre, farthest valid point
+      const int big = 0x7fffffff;
+      const float ox = 0.5f * (ord2f(__reduce_min_sync(0xffffffffu, valid ? f2ord(x) : big)) + ord2f(__reduce_max_sync(0xffffffffu, valid ? f2ord(x) : -big)));
+      const float oy = 0.5f * (ord2f(__reduce_min_sync(0xffffffffu, valid ? f2ord(y) : big)) + ord2f(__reduce_max_sync(0xffffffffu, valid ? f2ord(y) : -big)));
+      const float oz = 0.5f * (ord2f(__reduce_min_sync(0xffffffffu, valid ? f2ord(z) : big)) + ord2f(__reduce_max_sync(0xffffffffu, valid ? f2ord(z) : -big)));
+      const float ex = x - ox, ey = y - oy, ez = z - oz;
+      const float e2 = valid ? __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, ex * ex)) : 0.f;
+      const float R = sqrtf(__uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(e2)))) * 1.00001f;
+      // squared distance of every centre to the sphere centre (centre q * 32 + lane), and the smallest
+      float d2[kMaxQ];
+      float dmin = __int_as_float(0x7f800000);
 #pragma unroll
-    for (int q = 0; q < kMaxQ; ++q) {
-      if (q >= mq) break;
-      unsigned surv = __ballot_sync(0xffffffffu, lb[q] * 0.99999f <= thr);
-      while (surv) {
-        const int b = __ffs(surv) - 1;
-        surv &= surv - 1;
-        const int ci = q * 32 + b;
-        const float4 cc = s_c[ci];
-        const float dx = x - cc.x, dy = y - cc.y, dz = z - cc.z;
-        const float v = sqrtf(torch_sum3(dx * dx, dy * dy, dz * dz));   // channel ci + 1 (:144, :25-26)
-        if (v < best) { best = v; bi = ci + 1; }
+      for (int q = 0; q < kMaxQ; ++q) {
+        d2[q] = __int_as_float(0x7f800000);
+        if (q < mq) {
+          const float4 c = s_c[q * 32 + lane];
+          const float ax = c.x - ox, ay = c.y - oy, az = c.z - oz;
+          d2[q] = __fmaf_rn(az, az, __fmaf_rn(ay, ay, ax * ax));
+          dmin = fminf(dmin, d2[q]);                // NaN centres drop out here and below (comparisons are false)
+        }
       }
+      dmin = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(dmin)));
+      const float reach = sqrtf(dmin) * 1.00001f + 2.0f * R;
+      const float thr2 = reach * reach * 1.00001f;
+      int bi = 0;
+#pragma unroll
+      for (int q = 0; q < kMaxQ; ++q) {
+        if (q >= mq) break;
+        unsigned surv = __ballot_sync(0xffffffffu, d2[q] * 0.99999f <= thr2);
+        while (surv) {
+          const int b = __ffs(surv) - 1;
+          surv &= surv - 1;
+          const int ci = q * 32 + b;
+          const float4 cc = s_c[ci];
+          const float dx = x - cc.x, dy = y - cc.y, dz = z - cc.z;
+          const float v = sqrtf(torch_sum3(dx * dx, dy * dy, dz * dz));   // channel ci + 1 (:144, :25-26)
+          if (v < best) { best = v; bi = ci + 1; }
+        }
+      }
+      if (valid) label = bi > 0 ? bi + 1 : 0;          // :168-169
     }
-    if (valid) label = bi > 0 ? bi + 1 : 0;          // :168-169
+    if (inb) lb[p] = (uint8_t)label;
+    // ---- per-label count and exact range sum (range * 2^28 as u64, see the header), private bins
+    {
+      unsigned todo = __ballot_sync(0xffffffffu, inb);
+      const bool exact = !(inb && label >= 2) || (r >= 0.03125f && r < 256.0f);
+      if (!__all_sync(0xffffffffu, exact)) flag |= 1u;
+      const unsigned long long v = inb ? (unsigned long long)((double)r * 268435456.0) : 0ull;
+      while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int l = __shfl_sync(0xffffffffu, label, leader);
+        const bool mine = inb && label == l;
+        const unsigned grp = __ballot_sync(0xffffffffu, mine);
+        if (l >= 2) {
+          // v < 2^36: split so that 32 addends cannot overflow 32 bits
+          const unsigned slo = __reduce_add_sync(0xffffffffu, mine ? (unsigned)(v & 0xFFFFFu) : 0u);
+          const unsigned shi = __reduce_add_sync(0xffffffffu, mine ? (unsigned)(v >> 20) : 0u);
+          if (lane == leader) sum[l] += ((unsigned long long)shi << 20) + slo;
+        }
+        if (lane == leader) cnt[l] += (unsigned)__popc(grp);
+        todo &= ~grp;
+      }
+      __syncwarp();
+    }
+    // ---- contour bits inside the tile, its first pixel excluded (extract_contour, cpp_modules.cpp:534-545)
+    {
+      int left = __shfl_up_sync(0xffffffffu, label, 1);
+      if (lane == 0) left = carry;
+      carry = __shfl_sync(0xffffffffu, label, 31);
+      bool rowstart = false;
+      if (W >= 32) {
+        if (next_row < p0 + 32) { rowstart = (p == next_row); next_row += W; }
+      } else {
+        rowstart = (p % W) == 0;
+      }
+      const bool c = inb && p != p_tile && (rowstart || label != left);
+      ccnt += __popc(__ballot_sync(0xffffffffu, c));
+    }
   }
-  if (inb) labels[(size_t)f * HW + p] = (uint8_t)label;
-  warp_label_stats(label, inb, r, s_cnt, s_sum, s_flag);
-  tile_contour_count(label, inb, p, W, s_last, s_ccnt);
-  __syncthreads();
-  flush_tile_stats(K, f, tile, T, s_cnt, s_sum, s_flag, s_ccnt, bk);
+  // ---- flush the tile: histogram row, frame totals, contour count
+  for (int l = lane; l < K; l += 32) {
+    const unsigned c = cnt[l];
+    bk.tile_hist[((size_t)f * T + tile) * K + l] = (uint16_t)c;
+    if (c) {
+      atomicAdd(&bk.label_cnt[(size_t)f * K + l], c);
+      if (l >= 2) atomicAdd(&bk.label_sum[(size_t)f * K + l], sum[l]);
+    }
+  }
+  if (lane == 0) {
+    bk.tile_ccnt[(size_t)f * T + tile] = (uint16_t)ccnt;
+    if (flag) atomicOr(&bk.flags[f], flag);
+  }
 }
 
 // statistics only (caller-supplied labels)
@@ -184,9 +245,9 @@ extern "C" int rpcc_assign_labels_batch(const float* range, const float* lut, co
   const Book bk = make_book(book, B, T, K);
   int rc = zero_book(bk, B, K, st);
   if (rc != RPCC_OK) return rc;
-  const size_t smem = sizeof(float4) * 32 * ((m + 31) / 32) + (sizeof(unsigned long long) + sizeof(unsigned)) * K +
-                      sizeof(unsigned) * 34 + 16;
-  assign_labels_kernel<<<dim3(T, B), kTile, smem, st>>>(range, lut, ground, centers, HW, W, m, T, labels, bk);
+  const size_t smem = sizeof(float4) * 32 * ((m + 31) / 32) + (sizeof(unsigned long long) + sizeof(unsigned)) * K * kAsWarps;
+  assign_labels_kernel<<<dim3((T + kAsWarps - 1) / kAsWarps, B), kAsWarps * 32, smem, st>>>(range, lut, ground, centers, HW, W, m, T,
+                                                                                              labels, bk);
   RPCC_LAUNCH_CHECK("assign_labels_kernel");
   return RPCC_OK;
 }

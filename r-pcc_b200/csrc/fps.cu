@@ -559,7 +559,7 @@ extern "C" int rpcc_segment_fps_batch(const float* range, const float* lut, cons
   if (!use_cluster && m >= 2) {
     cudaStream_t st = as_stream(stream);
     const int NB = (HW + 31) / 32;
-    static const int minb = getenv("RPCC_FPS_MINB") ? atoi(getenv("RPCC_FPS_MINB")) : 1;
+    static const int minb = getenv("RPCC_FPS_MINB") ? atoi(getenv("RPCC_FPS_MINB")) : 2;
 #define RPCC_FPS_GO(T, Q, M) return launch_fps_pruned<T, Q, M>(range, lut, ground, B, HW, m, ground_thr, center_idx, centers, st)
     if (fps_threads == 512) {
       const int q = (NB + 511) / 512;
