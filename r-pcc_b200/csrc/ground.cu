@@ -17,18 +17,25 @@
 
 namespace rpcc {
 
-constexpr int kGfThreads = 1024;
+#ifndef RPCC_GF_THREADS
+#define RPCC_GF_THREADS 1024
+#endif
+#ifndef RPCC_GF_OCC
+#define RPCC_GF_OCC 1
+#endif
+constexpr int kGfThreads = RPCC_GF_THREADS;
 constexpr int kGfMaxPts = 5000;
 constexpr int kGfIters = 100;
 constexpr int kGfSample = 10;
 
-__global__ void __launch_bounds__(kGfThreads)
+__global__ void __launch_bounds__(kGfThreads, RPCC_GF_OCC)
 ground_fit_kernel(const float* __restrict__ range, const float* __restrict__ lut, int HW, unsigned long long seed,
                   float z_below, float inlier_thr, float* __restrict__ ground) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* px = reinterpret_cast<float*>(smem_raw);
   float* py = px + kGfMaxPts;
   float* pz = py + kGfMaxPts;
+  unsigned* s_mask = reinterpret_cast<unsigned*>(pz + kGfMaxPts);   // [NW][ceil(seg_len / 32)] candidate bits
   __shared__ int s_warp[kGfThreads / 32];
   __shared__ double s_plane[kGfIters][4];
   __shared__ unsigned long long s_score[kGfIters];  // (inliers << 32) | ~quantised rmse  (max wins)
@@ -45,11 +52,18 @@ ground_fit_kernel(const float* __restrict__ range, const float* __restrict__ lut
   const int seg_len = (HW + NW - 1) / NW;
   const int p_begin = warp * seg_len;
   const int p_end = min(HW, p_begin + seg_len);
-  // pass 1: count candidates (z < z_below; empty pixels have z = 0)
+  // pass 1: count candidates (z < z_below; empty pixels have z = 0) and remember them as one bit per pixel,
+  // in words private to the warp's segment
+  unsigned* wmask = s_mask + warp * ((seg_len + 31) / 32);
   int cnt = 0;
-  for (int p = p_begin + lane; p < p_end; p += 32) cnt += (rg[p] * lut[(size_t)p * 3 + 2] < z_below) ? 1 : 0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+#pragma unroll 4
+  for (int p0 = p_begin; p0 < p_end; p0 += 32) {
+    const int p = p0 + lane;
+    const bool c = p < p_end && (__ldg(rg + p) * __ldg(lut + 3 * p + 2) < z_below);
+    const unsigned b = __ballot_sync(0xffffffffu, c);
+    if (lane == 0) wmask[(p0 - p_begin) >> 5] = b;
+    cnt += __popc(b);
+  }
   if (lane == 0) s_warp[warp] = cnt;
   __syncthreads();
   int nc = 0, base = 0;
@@ -58,21 +72,18 @@ ground_fit_kernel(const float* __restrict__ range, const float* __restrict__ lut
   if (use_all) { nc = HW; base = p_begin; }
   const int ns = nc < kGfMaxPts ? nc : kGfMaxPts;
 
-  // pass 2: keep an even stride of the candidates, in raster order
+  // pass 2: keep an even stride of the candidates, in raster order; only the kept ones are loaded
   for (int p0 = p_begin; p0 < p_end; p0 += 32) {
     const int p = p0 + lane;
-    float x = 0.f, y = 0.f, z = 0.f;
-    bool cand = false;
-    if (p < p_end) {
-      const float r = rg[p];
-      x = r * lut[(size_t)p * 3]; y = r * lut[(size_t)p * 3 + 1]; z = r * lut[(size_t)p * 3 + 2];
-      cand = use_all || z < z_below;
-    }
-    const unsigned b = __ballot_sync(0xffffffffu, cand);
+    const unsigned b = use_all ? __ballot_sync(0xffffffffu, p < p_end) : wmask[(p0 - p_begin) >> 5];
+    const bool cand = (b >> lane) & 1u;
     if (cand) {
       const long long r = base + __popc(b & lanemask_lt());
       const int slot = (int)(r * ns / nc);
-      if (r == 0 || slot != (int)((r - 1) * ns / nc)) { px[slot] = x; py[slot] = y; pz[slot] = z; }
+      if (r == 0 || slot != (int)((r - 1) * ns / nc)) {
+        const float rr = __ldg(rg + p);
+        px[slot] = rr * __ldg(lut + 3 * p); py[slot] = rr * __ldg(lut + 3 * p + 1); pz[slot] = rr * __ldg(lut + 3 * p + 2);
+      }
     }
     base += __popc(b);
   }
@@ -171,7 +182,7 @@ extern "C" int rpcc_ground_fit_batch(const float* range, const float* lut, int B
                                      float* ground, void* stream) {
   RPCC_REQUIRE(range && lut && ground, "null pointer");
   if (B == 0) return RPCC_OK;
-  const size_t smem = sizeof(float) * 3 * kGfMaxPts;
+  const size_t smem = sizeof(float) * 3 * kGfMaxPts + sizeof(unsigned) * (size_t)(kGfThreads / 32) * (((H * W + kGfThreads / 32 - 1) / (kGfThreads / 32) + 31) / 32);
   RPCC_CUDA(cudaFuncSetAttribute(ground_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ground_fit_kernel<<<B, kGfThreads, smem, as_stream(stream)>>>(range, lut, H * W, (unsigned long long)seed, -1.5f, 0.1f, ground);
   RPCC_LAUNCH_CHECK("ground_fit_kernel");
