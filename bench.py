@@ -38,7 +38,9 @@ def parse():
     ap.add_argument("--frames", type=int, default=1184, help="frames per step per GPU (default 4 x 296)")
     ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic frames generated per GPU")
     ap.add_argument("--max-batch", type=int, default=296, help="frames per kernel launch (2 x 148 SMs)")
-    ap.add_argument("--e2e-frames", type=int, default=592)
+    ap.add_argument("--e2e-frames", type=int, default=1184)
+    ap.add_argument("--host-chunk", type=int, default=0,
+                    help="frames per upload/kernels/download pipeline stage of encode_host (0 = one per SM)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -227,7 +229,8 @@ def main():
     pts_np, off_np, g_np = make_workload(a.distinct, F, rank)
     npts = int(off_np[-1])
     max_chunk_pts = int(max(off_np[min(i + MB, F)] - off_np[i] for i in range(0, F, MB)))
-    enc = BatchEncoder(LIDAR, accuracy=0.02, max_batch=MB, max_points=max_chunk_pts, device=local)
+    enc = BatchEncoder(LIDAR, accuracy=0.02, max_batch=MB, max_points=max_chunk_pts, device=local,
+                       host_chunk=a.host_chunk)
     d_pts = torch.from_numpy(pts_np).cuda()
     d_off = torch.from_numpy(off_np).cuda()
     d_g = torch.from_numpy(g_np).cuda()
@@ -291,6 +294,17 @@ def main():
         h2d = int(h_pts.numel() * 4 + h_off.nbytes + (h_g.nbytes if h_g is not None else 0))
         enc.encode_host(h_pts, h_off, h_g)
         torch.cuda.synchronize()
+        # the PCIe link on its own: the same pinned points buffer uploaded by one plain copy (explains e2e)
+        d_tmp = torch.empty_like(d_pts[:h_pts.shape[0]])
+        d_tmp.copy_(h_pts, non_blocking=True)
+        torch.cuda.synchronize()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        d_tmp.copy_(h_pts, non_blocking=True)
+        l1.record()
+        torch.cuda.synchronize()
+        link_gbs = h_pts.numel() * 4 / (l0.elapsed_time(l1) / 1000.0) / 1e9
+        del d_tmp
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = max(2, a.steps)
@@ -312,7 +326,11 @@ def main():
                              g_np[:min(EF, 128)].copy() if a.inject_ground else None)
         rpcc_fps = min(EF, 128) / (time.perf_counter() - t0)
         e2e = {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "frames_per_step": EF, "with_host_bz2_frames_per_s": rpcc_fps, "host_threads": enc.workers,
+               "frames_per_step": EF, "h2d_link_gbs_plain_copy": link_gbs,
+               "h2d_achieved_gbs": h2d * reps / float(t2.item()) / 1e9,
+               "note": "bound by the upload of 16 B/point over PCIe; h2d_achieved_gbs / h2d_link_gbs_plain_copy is the "
+                       "fraction of the link this call keeps busy",
+               "with_host_bz2_frames_per_s": rpcc_fps, "host_threads": enc.workers,
                "mean_rpcc_bytes": float(np.mean([len(b) for b in blobs]))}
 
     if rank != 0:
@@ -352,8 +370,20 @@ def main():
             ent.update({"algorithmic_bytes_per_frame": alg[k], "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak})
         kernels[k] = ent
     pj = kernels.get("project", {})
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))["project_kernel"]
+            if int(tj["frames_per_launch"]) == int(round(pj.get("frames_per_launch", 0))):
+                traffic, traffic_src = float(tj["dram_bytes_per_launch"]), tj.get("capture")
+        except Exception:
+            pass
     roofline = {"kernel": "project_kernel", "bound": "hbm", "achieved": pj.get("achieved_gbs"), "peak": peak,
-                "unit": "GB/s", "frac": pj.get("frac_of_hbm_peak"), "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": pj.get("frac_of_hbm_peak"), "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": pj.get("algorithmic_bytes_per_frame", 0.0) * pj.get("frames_per_launch", 0.0),
+                "peak_source": peak_src,
                 "note": "dominant HBM mover of the chain (16 B/point in + 4 B/pixel out); the chain's time is dominated by "
                         "the latency/issue-bound FPS and label kernels, see kernels{}", "kernels": kernels}
 

@@ -272,6 +272,8 @@ typedef struct rpcc_encoder_config {
   int device;                  /* CUDA device ordinal */
   int model_method;            /* 0 = point (cfgs/compressor.yaml:29), 1 = plane */
   float plane_angle_threshold; /* degrees, cfgs/compressor.yaml:30 */
+  int host_chunk;              /* encode_host: frames per upload/kernels/download pipeline stage;
+                                  0 = one frame per SM of the device, always capped at max_batch */
 } rpcc_encoder_config;
 
 RPCC_API int rpcc_encoder_create(const rpcc_encoder_config* cfg, rpcc_encoder** out);
@@ -287,7 +289,9 @@ RPCC_API int rpcc_encoder_slots(void);
 RPCC_API int rpcc_encoder_encode_device(rpcc_encoder* enc, int slot, const float* points, int stride,
                                const int64_t* offsets, int B, const float* ground_in);
 /* Host inputs/outputs (bench `e2e`, and what tools/compress_datalist.py calls): any B; frames are
- * cut into chunks of max_batch and pipelined over the slots (upload / kernels / download overlap).
+ * cut into chunks of host_chunk (<= max_batch) and pipelined over the slots (upload / kernels / download
+ * overlap; the upload of ~1.9 MB per 64E frame over PCIe is what bounds this call, so the chunks are
+ * kept small enough that the link never idles behind a kernel batch).
  *   in : points_host rows of `stride` floats, offsets_host [B+1], ground_host [B][4] or NULL (fit on device)
  *   out: results [B]; model [B][K][4] f32; contour_bits [B][ceil(HW/8)]; seq: every frame's
  *        idx_sequence back to back (sum seq_count u16, capacity seq_cap entries); symbols likewise

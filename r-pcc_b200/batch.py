@@ -27,7 +27,7 @@ class _EncoderConfig(C.Structure):
                 ("level_dacc", C.c_double * 8), ("ground_level", C.c_int), ("feature_region", C.c_int),
                 ("segments", C.c_int), ("sharp_num", C.c_int), ("less_sharp_num", C.c_int), ("flat_num", C.c_int),
                 ("max_batch", C.c_int), ("max_points", C.c_int64), ("device", C.c_int),
-                ("model_method", C.c_int), ("plane_angle_threshold", C.c_float)]
+                ("model_method", C.c_int), ("plane_angle_threshold", C.c_float), ("host_chunk", C.c_int)]
 
 
 RESULT_DTYPE = np.dtype([("sym_count", np.uint32), ("seq_count", np.uint32), ("model_rows", np.uint32),
@@ -43,7 +43,7 @@ class BatchEncoder:
     batches of frames.  `accuracy` is the yaml value (step = 2 * accuracy, tools/compress.py:46)."""
 
     def __init__(self, lidar="Velodyne64E", accuracy=None, nonuniform=None, compressor_cfg=None, max_batch=256,
-                 max_points=None, device=None, basic_compressor=None, workers=None, model_method=None):
+                 max_points=None, device=None, basic_compressor=None, workers=None, model_method=None, host_chunk=0):
         cfg = load_compressor_cfg(compressor_cfg) if not isinstance(compressor_cfg, dict) else compressor_cfg
         self.cfg = cfg
         self.model_method = model_method or cfg["modeling_method"]
@@ -84,6 +84,7 @@ class BatchEncoder:
         c.device = self.device
         c.model_method = 1 if self.model_method == "plane" else 0
         c.plane_angle_threshold = float(cfg["plane_angle_threshold"])
+        c.host_chunk = int(host_chunk)
         self._c = c
         self._h = C.c_void_p(0)
         check(_lib.lib().rpcc_encoder_create(C.byref(c), C.byref(self._h)))

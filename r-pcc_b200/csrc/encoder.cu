@@ -62,6 +62,7 @@ constexpr int kEvRing = 256;   // chain calls per slot whose stage events are ke
 struct rpcc_encoder {
   rpcc_encoder_config cfg;
   int HW, K, T, cbytes;
+  int host_chunk;   // frames per pipeline stage of encode_host
   float hfov, vmax, vmin;
   float level_acc[8];
   float* lut = nullptr;
@@ -213,6 +214,12 @@ extern "C" int rpcc_encoder_create(const rpcc_encoder_config* cfg, rpcc_encoder*
   e->K = cfg->cluster_num + 2;
   e->T = (e->HW + RPCC_TILE - 1) / RPCC_TILE;
   e->cbytes = (e->HW + 7) / 8;
+  {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device) != cudaSuccess) { cudaGetLastError(); sms = 0; }
+    const int want = cfg->host_chunk > 0 ? cfg->host_chunk : (sms > 0 ? sms : cfg->max_batch);
+    e->host_chunk = want < cfg->max_batch ? want : cfg->max_batch;
+  }
   // the pybind boundary narrows the Python doubles to float (cpp_modules.cpp:427-428)
   e->hfov = (float)cfg->hfov; e->vmax = (float)cfg->vmax; e->vmin = (float)cfg->vmin;
   // QuantizationModule.__init__: acc = base + delta in f64 (utils/compress_utils.py:48), narrowed to
@@ -331,7 +338,7 @@ extern "C" int rpcc_encoder_encode_host(rpcc_encoder* e, const float* points_hos
   RPCC_REQUIRE(stride == 3 || stride == 4, "stride must be 3 or 4");
   RPCC_REQUIRE(B >= 0, "bad batch");
   RPCC_CUDA(cudaSetDevice(e->cfg.device));
-  const int MB = e->cfg.max_batch, K = e->K, cb = e->cbytes;
+  const int MB = e->host_chunk, K = e->K, cb = e->cbytes;
   const int nchunks = (B + MB - 1) / MB;
   size_t sym_done = 0, seq_done = 0;
   struct Pending { int slot, f0, nb; };

@@ -205,6 +205,20 @@ def test_encoder_device_path_and_ground_fit(R):
             assert symbols[sym_base[b]:sym_base[b + 1]].tobytes() == want["sections"]["residual_quantized"]
 
 
+def test_encode_host_is_independent_of_the_pipeline_chunking(R):
+    """encode_host cuts a call into host_chunk-frame pipeline stages; every section (including the ground
+    plane fitted on the device, keyed by the frame's index within the call) must not depend on the cut."""
+    from rpcc_b200 import synthetic
+    from rpcc_b200.batch import BatchEncoder
+    pts, off, _ = synthetic.batch(list(range(60, 67)), "Velodyne64E")
+    got = []
+    for chunk in (7, 2, 3):
+        with BatchEncoder("Velodyne64E", accuracy=0.02, max_batch=7, host_chunk=chunk) as enc:
+            out = enc.encode_host(pts, off, None)
+            got.append([BatchEncoder.frame_sections(out, b) for b in range(7)])
+    assert got[0] == got[1] == got[2]
+
+
 # ------------------------------------------------------------------------------------ L3 mirror + tools
 def test_l3_mirror_single_frame_compress_decompress_eval(R, example_points, gold, tmp_path):
     """The reference's single-frame flow (tools/compress.py --eval, tools/decompress.py) through the mirrored
