@@ -41,6 +41,7 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
   } while (0)
 
 int sm_count();
+int scratch_pool(cudaMemPool_t* out);   // library-owned stream-ordered pool of the current device
 
 // streaming (read-once) loads / L2-coherent loads
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {

@@ -2,6 +2,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <atomic>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -35,6 +36,37 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+// Stream-ordered scratch comes from a pool owned by the library, one per device, that keeps its memory
+// across synchronisation points (release threshold = max).  The device's default pool hands everything
+// back to the driver at every event/stream synchronisation -- which the pipelined host path does once
+// per chunk -- and re-mapping ~100 MB per launch stalls the copy queue.
+int scratch_pool(cudaMemPool_t* out) {
+  static std::mutex mu;
+  static cudaMemPool_t pools[64] = {nullptr};
+  int dev = 0;
+  RPCC_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) { set_error("scratch_pool: device ordinal %d out of range", dev); return RPCC_ERR_ARG; }
+  std::lock_guard<std::mutex> lock(mu);
+  if (!pools[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool = nullptr;
+    RPCC_CUDA(cudaMemPoolCreate(&pool, &props));
+    unsigned long long keep = ~0ull;
+    RPCC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    // a block freed on one stream is reused on another only once that free has completed: never by making
+    // the second stream wait for the first (the encoder's stream slots must stay independent)
+    int off = 0;
+    RPCC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off));
+    pools[dev] = pool;
+  }
+  *out = pools[dev];
+  return RPCC_OK;
 }
 
 }  // namespace rpcc

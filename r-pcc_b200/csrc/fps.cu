@@ -523,7 +523,9 @@ static int launch_fps_pruned(const float* range, const float* lut, const float* 
   if (grid > B) grid = B;
   // running distances of the frames in flight: stream-ordered scratch, no synchronisation
   void* ws = nullptr;
-  RPCC_CUDA(cudaMallocAsync(&ws, sizeof(unsigned) * (size_t)grid * HW, st));
+  cudaMemPool_t pool = nullptr;
+  { const int rc = scratch_pool(&pool); if (rc != RPCC_OK) return rc; }
+  RPCC_CUDA(cudaMallocFromPoolAsync(&ws, sizeof(unsigned) * (size_t)grid * HW, pool, st));
   kern<<<grid, THREADS, smem, st>>>(range, lut, ground, B, HW, m, thr, static_cast<unsigned*>(ws), center_idx, centers);
   const cudaError_t le = cudaGetLastError();
   RPCC_CUDA(cudaFreeAsync(ws, st));

@@ -71,6 +71,7 @@ ground_fit_kernel(const float* __restrict__ range, const float* __restrict__ lut
   const bool use_all = nc < 800;  // segment_utils.py:105-106
   if (use_all) { nc = HW; base = p_begin; }
   const int ns = nc < kGfMaxPts ? nc : kGfMaxPts;
+  const bool narrow = (unsigned long long)HW * (unsigned long long)kGfMaxPts < 0xFFFFFFFFull;
 
   // pass 2: keep an even stride of the candidates, in raster order; only the kept ones are loaded
   for (int p0 = p_begin; p0 < p_end; p0 += 32) {
@@ -78,9 +79,21 @@ ground_fit_kernel(const float* __restrict__ range, const float* __restrict__ lut
     const unsigned b = use_all ? __ballot_sync(0xffffffffu, p < p_end) : wmask[(p0 - p_begin) >> 5];
     const bool cand = (b >> lane) & 1u;
     if (cand) {
-      const long long r = base + __popc(b & lanemask_lt());
-      const int slot = (int)(r * ns / nc);
-      if (r == 0 || slot != (int)((r - 1) * ns / nc)) {
+      // candidate number r goes to slot floor(r * ns / nc) and is kept if it is the first one there
+      const int r = base + __popc(b & lanemask_lt());
+      int slot = r;
+      bool keep = true;
+      if (ns != nc) {
+        if (narrow) {   // r * ns < 2^32: one 32-bit division each instead of the 64-bit routine
+          const unsigned a = (unsigned)r * (unsigned)ns;
+          slot = (int)(a / (unsigned)nc);
+          keep = r == 0 || slot != (int)((a - (unsigned)ns) / (unsigned)nc);
+        } else {
+          slot = (int)((long long)r * ns / nc);
+          keep = r == 0 || slot != (int)((long long)(r - 1) * ns / nc);
+        }
+      }
+      if (keep) {
         const float rr = __ldg(rg + p);
         px[slot] = rr * __ldg(lut + 3 * p); py[slot] = rr * __ldg(lut + 3 * p + 1); pz[slot] = rr * __ldg(lut + 3 * p + 2);
       }
@@ -92,12 +105,22 @@ ground_fit_kernel(const float* __restrict__ range, const float* __restrict__ lut
   // hypotheses: one warp each
   for (int it = warp; it < kGfIters; it += kGfThreads / 32) {
     double s[10];
+    // sample j is the (j+1)-th link of one splitmix64 chain: lane j walks the chain to its own link and
+    // reduces it modulo ns (the 64-bit remainder is the expensive part), lane 0 then adds the ten points in order
+    int myk = 0;
+    if (lane < kGfSample) {
+      unsigned long long st = splitmix64(splitmix64(seed + (unsigned long long)f) ^ ((unsigned long long)it << 40));
+      for (int j = 0; j <= lane; ++j) st = splitmix64(st);
+      myk = (int)(st % (unsigned long long)ns);
+    }
+    int ks[kGfSample];
+#pragma unroll
+    for (int j = 0; j < kGfSample; ++j) ks[j] = __shfl_sync(0xffffffffu, myk, j);
     if (lane == 0) {
       for (int q = 0; q < 10; ++q) s[q] = 0.0;
-      unsigned long long st = splitmix64(splitmix64(seed + (unsigned long long)f) ^ ((unsigned long long)it << 40));
+#pragma unroll
       for (int j = 0; j < kGfSample; ++j) {
-        st = splitmix64(st);
-        const int k = (int)(st % (unsigned long long)ns);
+        const int k = ks[j];
         const double x = px[k], y = py[k], z = pz[k];
         s[0] += 1.0; s[1] += x; s[2] += y; s[3] += z;
         s[4] += x * x; s[5] += x * y; s[6] += x * z; s[7] += y * y; s[8] += y * z; s[9] += z * z;
