@@ -28,10 +28,11 @@ constexpr int kQThreads = kQWarps * 32;
 constexpr int kQSlices = RPCC_QSLICES;      // 32-pixel slices per step: that many independent loads in flight per lane
 constexpr int kQSteps = RPCC_TILE / (32 * kQSlices);
 
-__device__ __forceinline__ float predict_range(const float4 m, const float* __restrict__ lut3) {
-  // cpp_modules.cpp:271-279
-  if (m.x + m.y + m.z == 0) return m.w;
-  return -m.w / (m.x * lut3[0] + m.y * lut3[1] + m.z * lut3[2]);
+// Per-label table staged in shared memory: .x = the constant prediction m.w, .y = step, .z = 1 / step,
+// .w = 1 if the row is a plane (m.x + m.y + m.z != 0, cpp_modules.cpp:271), else 0.
+__device__ __forceinline__ float predict_plane(const float4 m, const float* __restrict__ lut3) {
+  // cpp_modules.cpp:273-279
+  return -m.w / (m.x * __ldg(lut3) + m.y * __ldg(lut3 + 1) + m.z * __ldg(lut3 + 2));
 }
 
 // One warp walks one tile in raster order, 32 consecutive pixels (a slice) at a time, and needs no
@@ -39,54 +40,30 @@ __device__ __forceinline__ float predict_range(const float4 m, const float* __re
 // in the frame's label-major symbol stream, of the tile's first symbol of that label) and advance as the
 // slices go by, so that the stable rank of a pixel is counter + (same-label lanes below it) -- one
 // match_any per slice.  Contour bits come from one ballot per slice, MSB-first bytes from brev.
-template <typename SymT>
-__global__ void __launch_bounds__(kQThreads, RPCC_QOCC)
-quantize_pack_kernel(const float* __restrict__ range, const uint8_t* __restrict__ labels, const float* __restrict__ model,
-                     const float* __restrict__ lut, Book bk, const float* __restrict__ step_per_label, float step,
-                     int HW, int W, int K, int T, SymT* __restrict__ symbols, size_t sym_stride,
-                     uint8_t* __restrict__ contour_bits, int cbytes, uint16_t* __restrict__ seq, size_t seq_stride,
-                     const unsigned long long* __restrict__ sym_base, const unsigned long long* __restrict__ seq_base) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* s_model = reinterpret_cast<float4*>(smem_raw);            // [K]
-  float2* s_step = reinterpret_cast<float2*>(s_model + K);          // [K] step, 1 / step
-  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_step + K);        // [kQWarps][K] next symbol position per label
-
-  const int f = blockIdx.y, tid = threadIdx.x;
-  const unsigned lane = tid & 31, warp = tid >> 5;
-  const int tile = blockIdx.x * kQWarps + (int)warp;
-  for (int l = tid; l < K; l += kQThreads) {
-    s_model[l] = reinterpret_cast<const float4*>(model)[(size_t)f * K + l];
-    const float st = step_per_label ? step_per_label[(size_t)f * K + l] : step;
-    s_step[l] = make_float2(st, 1.0f / st);
-  }
-  unsigned* cnt = s_cnt + warp * K;
-  if (tile < T)
-    for (int l = lane; l < K; l += 32) cnt[l] = bk.tile_off[((size_t)f * T + tile) * K + l];
-  __syncthreads();
-  if (tile >= T) return;
-
-  const size_t fbase = (size_t)f * HW;
-  const float* rg = range + fbase;
-  const uint8_t* lb = labels + fbase;
-  SymT* sym = symbols + (sym_base ? (size_t)sym_base[f] : (size_t)f * sym_stride);
-  uint16_t* sq = seq + (seq_base ? (size_t)seq_base[f] : (size_t)f * seq_stride) + bk.tile_coff[(size_t)f * T + tile];
-  uint8_t* cbits = contour_bits + (size_t)f * cbytes;
-  const int p_tile = tile * RPCC_TILE;
+// FULL: the whole tile lies inside the image (no bounds predicates).
+template <typename SymT, bool FULL>
+__device__ __forceinline__ void quantize_tile(const float* __restrict__ rg, const uint8_t* __restrict__ lb,
+                                              const float* __restrict__ lut, const float4* __restrict__ s_model,
+                                              const float4* __restrict__ s_tab, unsigned* __restrict__ cnt,
+                                              SymT* __restrict__ sym, uint16_t* __restrict__ sq,
+                                              uint8_t* __restrict__ cbits, int cbytes, int p_tile, int HW, int W, int K,
+                                              unsigned lane) {
   // label left of the tile's first pixel (-1: none, the pixel starts a run anyway)
   int carry = (p_tile > 0 && p_tile < HW) ? (int)lb[p_tile - 1] : -1;
   int next_row = ((p_tile + W - 1) / W) * W;     // next pixel that starts an image row (cpp_modules.cpp:537)
   unsigned nseq = 0;                             // idx_sequence entries emitted by this tile so far
+  const unsigned lt = lanemask_lt();
 
 #pragma unroll 1
   for (int s = 0; s < kQSteps; ++s) {
     const int p_step = p_tile + s * (32 * kQSlices);
-    if (p_step >= HW) break;
+    if (!FULL && p_step >= HW) break;
     float r[kQSlices];
     int lab[kQSlices];
 #pragma unroll
     for (int j = 0; j < kQSlices; ++j) {
       const int p = p_step + j * 32 + (int)lane;
-      const bool inb = p < HW;
+      const bool inb = FULL || p < HW;
       r[j] = inb ? ld_stream_f(rg + p) : 0.f;
       lab[j] = inb ? (int)__ldg(lb + p) : 1;
     }
@@ -94,31 +71,28 @@ quantize_pack_kernel(const float* __restrict__ range, const uint8_t* __restrict_
 #pragma unroll
     for (int j = 0; j < kQSlices; ++j) {
       const int p0 = p_step + j * 32, p = p0 + (int)lane;
-      const bool inb = p < HW;
+      const bool inb = FULL || p < HW;
       int l = lab[j];
       if (l >= K) l = 1;  // flagged by label_stats; never emitted
       // ---- symbol (cpp_modules.cpp:264-281, tools/compress.py:106, cpp_modules.cpp:311-331)
-      int q = 0;
-      if (l != 1) {
-        const float pred = predict_range(s_model[l], lut + (size_t)p * 3);
-        const float res = r[j] - pred;
-        // q = (int)roundf(res / step) (cpp_modules.cpp:318): the reciprocal product is within 1.8e-7 |t| of the
-        // IEEE quotient, so unless it lies within 1e-6 |t| of a rounding boundary (k + 0.5) both round to the
-        // same integer; the few that do (and NaN / huge values) take the division
-        const float2 st = s_step[l];
-        const float t = res * st.y, at = fabsf(t);
-        const float fl = floorf(at + 0.5f), d = (at + 0.5f) - fl;
-        if (fminf(d, 1.0f - d) > at * 1e-6f) q = t < 0.0f ? -(int)fl : (int)fl;
-        else q = (int)roundf(res / st.x);
-      }
+      const float4 tb = s_tab[l];
+      float pred = tb.x;
+      if (tb.w != 0.0f) pred = predict_plane(s_model[l], lut + (size_t)p * 3);
+      const float res = r[j] - pred;
+      // q = (int)roundf(res / step) (cpp_modules.cpp:318).  The reciprocal product t is within 1.8e-7 |t| of the
+      // IEEE quotient, so unless t lies within 1e-6 |t| of a rounding boundary (k + 0.5) both round to the same
+      // integer -- and away from a boundary round-to-nearest-even IS round-half-away.  The few that are near
+      // (and NaN / huge values, whose conversion does not round-trip) take the division.
+      const float t = res * tb.z;
+      int q = __float2int_rn(t);
+      if (!(__fmaf_rn(fabsf(t), 1e-6f, fabsf(t - (float)q)) < 0.5f)) q = (int)roundf(res / tb.y);
       // ---- stable position: private counter + rank among the slice's lanes with the same label
       const unsigned grp = __match_any_sync(0xffffffffu, l);
-      const int leader = __ffs(grp) - 1;
-      unsigned base = 0;
-      if ((int)lane == leader) { base = cnt[l]; cnt[l] = base + __popc(grp); }
-      base = __shfl_sync(0xffffffffu, base, leader);
+      const unsigned base = cnt[l];                  // same address for the whole group: one broadcast read
       __syncwarp();
-      if (l != 1) sym[(int)(base + __popc(grp & lanemask_lt()))] = (SymT)q;  // int16: wraps like astype(np.int16)
+      if ((grp & lt) == 0u) cnt[l] = base + __popc(grp);   // the group's lowest lane
+      __syncwarp();
+      if (l != 1) sym[base + __popc(grp & lt)] = (SymT)q;  // int16: wraps like astype(np.int16)
       // ---- contour bit (cpp_modules.cpp:534-545) and idx_sequence
       int left = __shfl_up_sync(0xffffffffu, l, 1);
       if (lane == 0) left = carry;
@@ -129,14 +103,15 @@ quantize_pack_kernel(const float* __restrict__ range, const uint8_t* __restrict_
       } else {
         rowstart = (p % W) == 0;
       }
-      const unsigned cb = __ballot_sync(0xffffffffu, inb && (rowstart || l != left));
-      if ((cb >> lane) & 1u) sq[(int)(nseq + __popc(cb & lanemask_lt()))] = (uint16_t)l;
+      const bool c = inb && (rowstart || l != left);
+      const unsigned cb = __ballot_sync(0xffffffffu, c);
+      if (c) sq[nseq + __popc(cb & lt)] = (uint16_t)l;
       nseq += __popc(cb);
       words[j] = __byte_perm(__brev(cb), 0, 0x0123);   // np.packbits: pixel p0+i -> byte i/8, bit 7-(i%8)
     }
     // ---- contour bytes of the step: 4 bytes per slice
     const int byte0 = p_step >> 3;
-    if ((cbytes & 15) == 0 && byte0 + 4 * kQSlices <= cbytes) {        // every frame's bitmap is 16-byte aligned
+    if ((cbytes & 15) == 0 && (FULL || byte0 + 4 * kQSlices <= cbytes)) {        // every frame's bitmap is 16-byte aligned
       if (lane == 0) {
         uint4* dst = reinterpret_cast<uint4*>(cbits + byte0);
 #pragma unroll
@@ -156,6 +131,45 @@ quantize_pack_kernel(const float* __restrict__ range, const uint8_t* __restrict_
       }
     }
   }
+}
+
+template <typename SymT>
+__global__ void __launch_bounds__(kQThreads, RPCC_QOCC)
+quantize_pack_kernel(const float* __restrict__ range, const uint8_t* __restrict__ labels, const float* __restrict__ model,
+                     const float* __restrict__ lut, Book bk, const float* __restrict__ step_per_label, float step,
+                     int HW, int W, int K, int T, SymT* __restrict__ symbols, size_t sym_stride,
+                     uint8_t* __restrict__ contour_bits, int cbytes, uint16_t* __restrict__ seq, size_t seq_stride,
+                     const unsigned long long* __restrict__ sym_base, const unsigned long long* __restrict__ seq_base) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* s_model = reinterpret_cast<float4*>(smem_raw);            // [K]
+  float4* s_tab = s_model + K;                                      // [K] constant prediction, step, 1 / step, plane flag
+  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_tab + K);         // [kQWarps][K] next symbol position per label
+
+  const int f = blockIdx.y, tid = threadIdx.x;
+  const unsigned lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x * kQWarps + (int)warp;
+  for (int l = tid; l < K; l += kQThreads) {
+    const float4 m = reinterpret_cast<const float4*>(model)[(size_t)f * K + l];
+    s_model[l] = m;
+    const float st = step_per_label ? step_per_label[(size_t)f * K + l] : step;
+    s_tab[l] = make_float4(m.w, st, 1.0f / st, (m.x + m.y + m.z == 0) ? 0.0f : 1.0f);
+  }
+  unsigned* cnt = s_cnt + warp * K;
+  if (tile < T)
+    for (int l = lane; l < K; l += 32) cnt[l] = bk.tile_off[((size_t)f * T + tile) * K + l];
+  __syncthreads();
+  if (tile >= T) return;
+
+  const size_t fbase = (size_t)f * HW;
+  SymT* sym = symbols + (sym_base ? (size_t)sym_base[f] : (size_t)f * sym_stride);
+  uint16_t* sq = seq + (seq_base ? (size_t)seq_base[f] : (size_t)f * seq_stride) + bk.tile_coff[(size_t)f * T + tile];
+  const int p_tile = tile * RPCC_TILE;
+  if (p_tile + RPCC_TILE <= HW)
+    quantize_tile<SymT, true>(range + fbase, labels + fbase, lut, s_model, s_tab, cnt, sym, sq,
+                              contour_bits + (size_t)f * cbytes, cbytes, p_tile, HW, W, K, lane);
+  else
+    quantize_tile<SymT, false>(range + fbase, labels + fbase, lut, s_model, s_tab, cnt, sym, sq,
+                               contour_bits + (size_t)f * cbytes, cbytes, p_tile, HW, W, K, lane);
 }
 
 // exclusive scan of the per-frame symbol / sequence counts (one CTA; B <= 65535)
@@ -216,7 +230,7 @@ int quantize_pack_launch(const float* range, const uint8_t* labels, const float*
   if (B == 0) return RPCC_OK;
   const int HW = H * W, T = (HW + RPCC_TILE - 1) / RPCC_TILE;
   const Book bk = make_book(book, B, T, K);
-  const size_t smem = (sizeof(float4) + sizeof(float2)) * K + sizeof(unsigned) * (size_t)kQWarps * K;
+  const size_t smem = 2 * sizeof(float4) * K + sizeof(unsigned) * (size_t)kQWarps * K;
   quantize_pack_kernel<SymT><<<dim3((T + kQWarps - 1) / kQWarps, B), kQThreads, smem, as_stream(stream)>>>(
       range, labels, model, lut, bk, step_per_label, step, HW, W, K, T, symbols, sym_stride, contour_bits,
       (HW + 7) / 8, seq, seq_stride, reinterpret_cast<const unsigned long long*>(sym_base),
