@@ -28,6 +28,7 @@ constexpr int kMaxQ = 8;          // centres per lane in the bound pass: up to 2
 // order-preserving float <-> int maps, so that the warp-wide REDUX min / max work on floats
 __device__ __forceinline__ int f2ord(float f) { const int b = __float_as_int(f); return b ^ ((b >> 31) & 0x7fffffff); }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+__device__ __forceinline__ float sqrt_approx(float v) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
 
 constexpr int kAsWarps = 8;        // one 1024-pixel tile per warp, 8 tiles of one frame per CTA
 
@@ -41,13 +42,14 @@ constexpr int kAsWarps = 8;        // one 1024-pixel tile per warp, 8 tiles of o
 // above the rounding of the quantities compared, so a culled centre can neither win nor tie.
 // Label statistics go to per-warp bins in shared memory (no atomics: one leader lane per label and
 // slice) and are flushed once per tile.
+template <int MQ>   // centres per lane in the bound pass (32 * MQ >= m; the padding sits at +inf)
 __global__ void __launch_bounds__(kAsWarps * 32, 6)
 assign_labels_kernel(const float* __restrict__ range, const float* __restrict__ lut, const float* __restrict__ ground,
                      const float* __restrict__ centers, int HW, int W, int m, int T, uint8_t* __restrict__ labels, Book bk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int K = m + 2;
-  const int mq = (m + 31) / 32;                                                    // centres per lane
-  float4* s_c = reinterpret_cast<float4*>(smem_raw);                               // [mq * 32] x, y, z, -
+  constexpr int mq = MQ;
+  float4* s_c = reinterpret_cast<float4*>(smem_raw);                               // [MQ * 32] x, y, z, -
   unsigned long long* s_sum = reinterpret_cast<unsigned long long*>(s_c + mq * 32); // [kAsWarps][K]
   unsigned* s_cnt = reinterpret_cast<unsigned*>(s_sum + kAsWarps * K);            // [kAsWarps][K]
 
@@ -99,27 +101,24 @@ assign_labels_kernel(const float* __restrict__ range, const float* __restrict__ 
       const float oz = 0.5f * (ord2f(__reduce_min_sync(0xffffffffu, valid ? f2ord(z) : big)) + ord2f(__reduce_max_sync(0xffffffffu, valid ? f2ord(z) : -big)));
       const float ex = x - ox, ey = y - oy, ez = z - oz;
       const float e2 = valid ? __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, ex * ex)) : 0.f;
-      const float R = sqrtf(__uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(e2)))) * 1.00001f;
+      // (bounds only: the approximate square root's 2 ulp disappear in the 1e-5 slack)
+      const float R = sqrt_approx(__uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(e2)))) * 1.00001f;
       // squared distance of every centre to the sphere centre (centre q * 32 + lane), and the smallest
-      float d2[kMaxQ];
+      float d2[MQ];
       float dmin = __int_as_float(0x7f800000);
 #pragma unroll
-      for (int q = 0; q < kMaxQ; ++q) {
-        d2[q] = __int_as_float(0x7f800000);
-        if (q < mq) {
-          const float4 c = s_c[q * 32 + lane];
-          const float ax = c.x - ox, ay = c.y - oy, az = c.z - oz;
-          d2[q] = __fmaf_rn(az, az, __fmaf_rn(ay, ay, ax * ax));
-          dmin = fminf(dmin, d2[q]);                // NaN centres drop out here and below (comparisons are false)
-        }
+      for (int q = 0; q < MQ; ++q) {
+        const float4 c = s_c[q * 32 + lane];
+        const float ax = c.x - ox, ay = c.y - oy, az = c.z - oz;
+        d2[q] = __fmaf_rn(az, az, __fmaf_rn(ay, ay, ax * ax));
+        dmin = fminf(dmin, d2[q]);                  // NaN centres drop out here and below (comparisons are false)
       }
       dmin = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(dmin)));
-      const float reach = sqrtf(dmin) * 1.00001f + 2.0f * R;
+      const float reach = sqrt_approx(dmin) * 1.00001f + 2.0f * R;
       const float thr2 = reach * reach * 1.00001f;
       int bi = 0;
 #pragma unroll
-      for (int q = 0; q < kMaxQ; ++q) {
-        if (q >= mq) break;
+      for (int q = 0; q < MQ; ++q) {
         unsigned surv = __ballot_sync(0xffffffffu, d2[q] * 0.99999f <= thr2);
         while (surv) {
           const int b = __ffs(surv) - 1;
@@ -245,9 +244,13 @@ extern "C" int rpcc_assign_labels_batch(const float* range, const float* lut, co
   const Book bk = make_book(book, B, T, K);
   int rc = zero_book(bk, B, K, st);
   if (rc != RPCC_OK) return rc;
-  const size_t smem = sizeof(float4) * 32 * ((m + 31) / 32) + (sizeof(unsigned long long) + sizeof(unsigned)) * K * kAsWarps;
-  assign_labels_kernel<<<dim3((T + kAsWarps - 1) / kAsWarps, B), kAsWarps * 32, smem, st>>>(range, lut, ground, centers, HW, W, m, T,
-                                                                                              labels, bk);
+  const int mq = (m + 31) / 32;
+  const int MQ = mq <= 1 ? 1 : mq <= 2 ? 2 : mq <= 4 ? 4 : 8;
+  const size_t smem = sizeof(float4) * 32 * MQ + (sizeof(unsigned long long) + sizeof(unsigned)) * K * kAsWarps;
+  const dim3 grid((T + kAsWarps - 1) / kAsWarps, B);
+#define RPCC_ASSIGN_GO(Q) assign_labels_kernel<Q><<<grid, kAsWarps * 32, smem, st>>>(range, lut, ground, centers, HW, W, m, T, labels, bk)
+  if (MQ == 1) RPCC_ASSIGN_GO(1); else if (MQ == 2) RPCC_ASSIGN_GO(2); else if (MQ == 4) RPCC_ASSIGN_GO(4); else RPCC_ASSIGN_GO(8);
+#undef RPCC_ASSIGN_GO
   RPCC_LAUNCH_CHECK("assign_labels_kernel");
   return RPCC_OK;
 }

@@ -377,18 +377,25 @@ __device__ __forceinline__ float ordf(int i) { return __int_as_float(i ^ ((i >> 
 template <int THREADS, int Q, int MINB>   // Q buckets per lane: the warp owns buckets warp + NW * (q * 32 + lane)
 __global__ void __launch_bounds__(THREADS, MINB)
 segment_fps_pruned_kernel(const float* __restrict__ range, const float* __restrict__ lut, const float* __restrict__ ground,
-                          int B, int HW, int m, float thr, unsigned* __restrict__ temp_ws, int* __restrict__ center_idx,
-                          float* __restrict__ centers) {
+                          int B, int HW, int m, float thr, unsigned* __restrict__ temp_ws, int* __restrict__ next_frame,
+                          int* __restrict__ center_idx, float* __restrict__ centers) {
   constexpr int NW = THREADS / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int NB = (HW + 31) >> 5;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_box = reinterpret_cast<float*>(smem_raw);            // [6][Q][THREADS]: x0,y0,z0,x1,y1,z1 of bucket (q, tid)
   __shared__ uint2 s_part[2][32];
+  __shared__ int s_frame;
   unsigned* temp = temp_ws + (size_t)blockIdx.x * HW;
   const float INF = __int_as_float(0x7f800000);
 
-  for (int f = blockIdx.x; f < B; f += gridDim.x) {
+  // Frames are handed out by a counter: the number of bucket updates (and so the time) differs by tens of per cent
+  // from frame to frame, and a static round-robin leaves the SMs with the short frames idle at the end of the launch.
+  for (;;) {
+    if (tid == 0) s_frame = atomicAdd(next_frame, 1);
+    __syncthreads();
+    const int f = s_frame;
+    if (f >= B) break;
     const float* rg = range + (size_t)f * HW;
     const float g0 = ground[f * 4], g1 = ground[f * 4 + 1], g2 = ground[f * 4 + 2], g3 = ground[f * 4 + 3];
     const float gnorm = sqrtf(torch_sum3(g0 * g0, g1 * g1, g2 * g2));
@@ -506,7 +513,7 @@ segment_fps_pruned_kernel(const float* __restrict__ range, const float* __restri
         }
       }
     }
-    __syncthreads();   // the next frame's first pass rewrites temp[] and s_part
+    __syncthreads();   // the next frame's first pass rewrites temp[], s_part and s_frame
   }
 }
 
@@ -525,9 +532,14 @@ static int launch_fps_pruned(const float* range, const float* lut, const float* 
   void* ws = nullptr;
   cudaMemPool_t pool = nullptr;
   { const int rc = scratch_pool(&pool); if (rc != RPCC_OK) return rc; }
-  RPCC_CUDA(cudaMallocFromPoolAsync(&ws, sizeof(unsigned) * (size_t)grid * HW, pool, st));
-  kern<<<grid, THREADS, smem, st>>>(range, lut, ground, B, HW, m, thr, static_cast<unsigned*>(ws), center_idx, centers);
-  const cudaError_t le = cudaGetLastError();
+  const size_t ws_bytes = sizeof(unsigned) * (size_t)grid * HW;
+  RPCC_CUDA(cudaMallocFromPoolAsync(&ws, ws_bytes + 256, pool, st));
+  int* counter = reinterpret_cast<int*>(static_cast<unsigned char*>(ws) + ws_bytes);   // frame queue head
+  cudaError_t le = cudaMemsetAsync(counter, 0, sizeof(int), st);
+  if (le == cudaSuccess) {
+    kern<<<grid, THREADS, smem, st>>>(range, lut, ground, B, HW, m, thr, static_cast<unsigned*>(ws), counter, center_idx, centers);
+    le = cudaGetLastError();
+  }
   RPCC_CUDA(cudaFreeAsync(ws, st));
   RPCC_CUDA(le);
   count_launch();
