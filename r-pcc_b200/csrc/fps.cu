@@ -370,6 +370,9 @@ static int launch_segment_fps(const float* range, const float* lut, const float*
 //   state in global memory (L2-resident): t[HW] per CTA, bit 31 = "masked to the origin"
 //   state on chip: boxes in shared memory (6 floats per bucket), max t / tie key in registers.
 constexpr unsigned kNoTie = 0xFFFFFFFFu;
+#ifndef RPCC_FPS_WF
+#define RPCC_FPS_WF 1
+#endif
 
 __device__ __forceinline__ int ford(float f) { const int b = __float_as_int(f); return b ^ ((b >> 31) & 0x7fffffff); }
 __device__ __forceinline__ float ordf(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
@@ -463,9 +466,17 @@ segment_fps_pruned_kernel(const float* __restrict__ range, const float* __restri
         const unsigned dmax = __reduce_max_sync(0xffffffffu, v.x);
         const unsigned tkmin = __reduce_min_sync(0xffffffffu, v.x == dmax ? v.y : kNoTie);
         const int k = (int)(((tkmin & 0x3FFFFFu) << 10) | __brev(tkmin & 0xFFC00000u));
+#if RPCC_FPS_WF
+        // all five loads leave together (volatile asm: the compiler would otherwise predicate the last four on the first)
+        const float r = ld_stream_f(rg + k);
+        const float wx = ld_stream_f(lut + (size_t)k * 3), wy = ld_stream_f(lut + (size_t)k * 3 + 1), wz = ld_stream_f(lut + (size_t)k * 3 + 2);
+        const bool org = (temp[k] >> 31) != 0u;
+        x1 = org ? 0.f : r * wx; y1 = org ? 0.f : r * wy; z1 = org ? 0.f : r * wz;
+#else
         const bool org = (temp[k] >> 31) != 0u;
         const float r = rg[k];
         x1 = org ? 0.f : r * lut[(size_t)k * 3]; y1 = org ? 0.f : r * lut[(size_t)k * 3 + 1]; z1 = org ? 0.f : r * lut[(size_t)k * 3 + 2];
+#endif
         if (tid == 0) {
           center_idx[(size_t)f * m + j] = k;
           float* c = centers + ((size_t)f * m + j) * 3;
