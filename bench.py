@@ -35,9 +35,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=1184, help="frames per step per GPU (default 4 x 296)")
+    ap.add_argument("--frames", type=int, default=2368, help="frames per step per GPU (default 2 x 1184)")
     ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic frames generated per GPU")
-    ap.add_argument("--max-batch", type=int, default=296, help="frames per kernel launch (2 x 148 SMs)")
+    ap.add_argument("--max-batch", type=int, default=1184,
+                    help="frames per kernel launch (8 x 148 SMs: the one-CTA-per-frame kernels draw frames from a queue, "
+                         "so a long launch evens out the frame-to-frame spread of the FPS work)")
     ap.add_argument("--e2e-frames", type=int, default=1184)
     ap.add_argument("--host-chunk", type=int, default=0,
                     help="frames per upload/kernels/download pipeline stage of encode_host (0 = one per SM)")
