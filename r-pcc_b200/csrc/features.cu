@@ -32,6 +32,49 @@ __device__ __forceinline__ bool gap_accept(const float* __restrict__ rrow, int w
   return ok;
 }
 
+// Bitonic sort of 32 * E keys by one warp, in registers: element i = lane * E + r lives in register r of `lane`, so the
+// strides below E are compare-exchanges inside a lane and the others one shuffle per key; no shared-memory round trips
+// and no warp barriers between the stages.  Ascending, like std::sort on pair<float,int> (the keys are distinct).
+template <int E>
+__device__ __forceinline__ void warp_sort_regs(unsigned long long* __restrict__ key, int lane) {
+  unsigned long long v[E];
+#pragma unroll
+  for (int r = 0; r < E; ++r) v[r] = key[r * 32 + lane];        // any input order will do: conflict-free reads
+  __syncwarp();
+#pragma unroll
+  for (int k = 2; k <= 32 * E; k <<= 1) {
+#pragma unroll
+    for (int st = k >> 1; st > 0; st >>= 1) {
+      if (st < E) {
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+          if ((r & st) == 0) {
+            const bool up = ((lane * E + r) & k) == 0;
+            const unsigned long long a = v[r], b = v[r | st];
+            const bool sw = (a > b) == up;
+            v[r] = sw ? b : a;
+            v[r | st] = sw ? a : b;
+          }
+        }
+      } else {
+        const int ls = st / E;
+        const bool lower = (lane & ls) == 0;
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+          const bool up = ((lane * E + r) & k) == 0;
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, v[r], ls);
+          const bool keep_min = lower == up;
+          const bool other_smaller = other < v[r];
+          v[r] = (keep_min == other_smaller) ? other : v[r];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < E; ++r) key[lane * E + r] = v[r];
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(kFeatThreads)
 keypoints_kernel(const float* __restrict__ range, const uint8_t* __restrict__ labels, int H, int W, int K, int region,
                  int segments, int sharp_num, int less_sharp_num, int flat_num, int N,
@@ -104,16 +147,23 @@ keypoints_kernel(const float* __restrict__ range, const uint8_t* __restrict__ la
   for (int j = warp; j < segments; j += kFeatThreads / 32) {
     unsigned long long* key = s_key + (size_t)j * N;
     // bitonic sort, ascending; padding keys (~0) end up past `per`
-    for (int k = 2; k <= N; k <<= 1) {
-      for (int st = k >> 1; st > 0; st >>= 1) {
-        for (int i = lane; i < N / 2; i += 32) {
-          const int lo = ((i & ~(st - 1)) << 1) | (i & (st - 1));
-          const int hi = lo | st;
-          const bool up = (lo & k) == 0;
-          const unsigned long long a = key[lo], b = key[hi];
-          if ((a > b) == up) { key[lo] = b; key[hi] = a; }
+    if (N == 32) warp_sort_regs<1>(key, lane);
+    else if (N == 64) warp_sort_regs<2>(key, lane);
+    else if (N == 128) warp_sort_regs<4>(key, lane);
+    else if (N == 256) warp_sort_regs<8>(key, lane);
+    else if (N == 512) warp_sort_regs<16>(key, lane);
+    else {
+      for (int k = 2; k <= N; k <<= 1) {
+        for (int st = k >> 1; st > 0; st >>= 1) {
+          for (int i = lane; i < N / 2; i += 32) {
+            const int lo = ((i & ~(st - 1)) << 1) | (i & (st - 1));
+            const int hi = lo | st;
+            const bool up = (lo & k) == 0;
+            const unsigned long long a = key[lo], b = key[hi];
+            if ((a > b) == up) { key[lo] = b; key[hi] = a; }
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
     // sharp walk: largest curvature first (cpp_modules.cpp:79-95)

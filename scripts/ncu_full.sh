@@ -7,6 +7,6 @@ kernels=("$@")
 mkdir -p gpurun_out
 for k in "${kernels[@]}"; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f \
-    -o gpurun_out/${tag}_$k python scripts/profile_chain.py 296 ${REPS:-2} > gpurun_out/${tag}_$k.log 2>&1
+    -o gpurun_out/${tag}_$k python scripts/profile_chain.py ${FRAMES:-296} ${REPS:-2} > gpurun_out/${tag}_$k.log 2>&1
   tail -2 gpurun_out/${tag}_$k.log
 done
