@@ -172,6 +172,50 @@ def test_encoder_batches_match_oracle_and_roundtrip(R, lidar, nonuniform):
         assert float(np.abs(rec - wants[b]["range_image"]).max()) <= bound + 1e-5
 
 
+@pytest.mark.parametrize("lidar,nonuniform,B", [("Velodyne64E", False, 700), ("VelodyneVLP16", True, 1300)])
+def test_long_launch_every_cta_takes_several_frames(R, lidar, nonuniform, B):
+    """BASELINE full size and beyond: one launch of B frames (more than the 2 x 148 CTAs of the one-CTA-per-frame
+    kernels, so the FPS frame queue, the persistent projection teams and the ground fit all take several frames per
+    CTA).  The B slots are copies of 6 distinct frames in a scrambled order: every copy must produce the bytes of its
+    source frame, the distinct ones the oracle's, with the ground plane fitted on the device and injected alike."""
+    import torch
+    from rpcc_b200 import synthetic
+    from rpcc_b200.batch import BatchEncoder
+    nd = 6
+    per = [synthetic.frame(60 + i, lidar) for i in range(nd)]
+    order = [(i * 7 + i // 5) % nd for i in range(B)]
+    pts = np.concatenate([per[k][0] for k in order], 0)
+    off = np.cumsum([0] + [per[k][0].shape[0] for k in order]).astype(np.int64)
+    grounds = np.stack([per[k][1] for k in order]).astype(np.float32)
+    with BatchEncoder(lidar, accuracy=0.02, nonuniform=nonuniform, max_batch=B, max_points=pts.shape[0], host_chunk=B) as enc:
+        out = enc.encode_host(pts, off, grounds)
+        first = {}
+        for b in range(B):
+            sec = BatchEncoder.frame_sections(out, b)
+            k = order[b]
+            if k not in first:
+                first[k] = sec
+                want = oracle.compress_frame(per[k][0], lidar, per[k][1], nonuniform=nonuniform)["sections"]
+                for name, v in want.items():
+                    assert sec[name] == v, (lidar, b, name)
+            else:
+                assert sec == first[k], (lidar, b, k)
+        # device-fitted ground: deterministic per frame content + position-independent except for the RANSAC key
+        d_pts, d_off = torch.from_numpy(pts).cuda(), torch.from_numpy(off).cuda()
+        enc.encode_device(0, d_pts, d_off, B, None)
+        enc.sync()
+        sb = enc.device_buffer(0, "sym_base", (B + 1,), torch.int64).cpu().numpy()
+        sym1 = enc.device_buffer(0, "symbols", (int(sb[-1]),), torch.int16).cpu().numpy().copy()
+        g1 = enc.device_buffer(0, "ground", (B, 4), torch.float32).cpu().numpy().copy()
+        enc.encode_device(0, d_pts, d_off, B, None)
+        enc.sync()
+        sb2 = enc.device_buffer(0, "sym_base", (B + 1,), torch.int64).cpu().numpy()
+        assert np.array_equal(sb, sb2)
+        assert np.array_equal(sym1, enc.device_buffer(0, "symbols", (int(sb[-1]),), torch.int16).cpu().numpy())
+        assert np.array_equal(g1.view(np.uint32), enc.device_buffer(0, "ground", (B, 4), torch.float32).cpu().numpy().view(np.uint32))
+        assert np.isfinite(g1).all() and (np.abs(np.linalg.norm(g1[:, :3], axis=1) - 1.0) < 1e-4).all()
+
+
 def test_encoder_device_path_and_ground_fit(R):
     """Device-resident inputs, ground fitted on the device: deterministic, close to the true plane, and the
     rest of the chain is byte-exact against the oracle GIVEN that fitted plane."""
