@@ -56,59 +56,98 @@ contour_prefix_kernel(const uint8_t* __restrict__ contour_bits, int cbytes, int 
   }
 }
 
-__global__ void __launch_bounds__(kDTile, 2)
+constexpr int kDWarps = 8;   // one 1024-pixel tile per warp, 8 tiles of one frame per CTA (as assign.cu / quantize.cu)
+
+// One warp walks one tile, 32 pixels (one contour word) at a time; nothing is shared between the warps of a CTA, so
+// there is no block-level synchronisation.  label(p) = seq[contour bits in pixels 1..p]; the per-(tile,label) pixel counts
+// go to bins private to the warp (one leader lane per label and slice, found with match_any), the run count of the
+// decoded map is kept for validation (point_model_kernel compares it with the sequence length).
+__global__ void __launch_bounds__(kDWarps * 32, 6)
 decode_labels_kernel(const uint8_t* __restrict__ contour_bits, int cbytes, const uint16_t* __restrict__ seq,
                      size_t seq_stride, const uint32_t* __restrict__ seq_count, int HW, int W, int K, int T,
                      uint8_t* __restrict__ labels, Book bk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  unsigned long long* s_sum = reinterpret_cast<unsigned long long*>(smem_raw);
-  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_sum + K);
-  unsigned* s_flag = s_cnt + K;
-  unsigned* s_ccnt = s_flag + 1;
-  unsigned* s_wc = s_ccnt + 1;  // [32]
-  unsigned* s_last = s_wc + 32; // [32]
-  const int f = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+  unsigned* s_cnt = reinterpret_cast<unsigned*>(smem_raw);      // [kDWarps][K]
+  const int f = blockIdx.y, tid = threadIdx.x;
   const unsigned lane = tid & 31, warp = tid >> 5;
-  for (int l = tid; l < K; l += kDTile) { s_cnt[l] = 0; s_sum[l] = 0; }
-  if (tid == 0) { *s_flag = 0; *s_ccnt = 0; }
-  const int p = tile * kDTile + tid;
-  const bool inb = p < HW;
-  const int word = p >> 5;
-  unsigned v = 0;
-  if (word * 32 < HW) {
-    v = load_word_be(contour_bits + (size_t)f * cbytes, cbytes, word);
-    if (word == 0) v &= 0x7FFFFFFFu;
-  }
-  if (lane == 0) s_wc[warp] = __popc(v);
-  __syncthreads();
-  unsigned before = 0;
+  const int tile = blockIdx.x * kDWarps + (int)warp;
+  if (tile >= T) return;
+  unsigned* cnt = s_cnt + warp * K;
+  for (int l = lane; l < K; l += 32) cnt[l] = 0;
+  __syncwarp();
+
+  const int p_tile = tile * kDTile;
+  const uint8_t* bits = contour_bits + (size_t)f * cbytes;
+  // lane j holds the contour word of slice j (pixel i of a word is bit 31 - i; pixel 0 of the image never counts)
+  unsigned v_mine = 0;
   {
-    const unsigned wc = s_wc[lane];
-    unsigned incl = wc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned u = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= (unsigned)o) incl += u;
+    const int w = (p_tile >> 5) + (int)lane;
+    if (w * 32 < HW) {
+      v_mine = load_word_be(bits, cbytes, w);
+      if (w == 0) v_mine &= 0x7FFFFFFFu;
     }
-    before = __shfl_sync(0xffffffffu, incl - wc, warp);
   }
-  int label = 1;
-  if (inb) {
-    const unsigned idx = bk.tile_coff[(size_t)f * T + tile] + before + __popc(v >> (31 - lane));
-    const unsigned L = seq_count ? seq_count[f] : 0xFFFFFFFFu;
-    int l = idx < L ? (int)seq[(size_t)f * seq_stride + idx] : 1;
-    if (idx >= L) atomicOr(s_flag, 4u);            // sequence shorter than the contour map asks for
-    if (l >= K) { l = 1; atomicOr(s_flag, 2u); }   // label without a model row
-    label = l;
-    labels[(size_t)f * HW + p] = (uint8_t)label;
+  unsigned running = bk.tile_coff[(size_t)f * T + tile];
+  const unsigned L = seq_count ? seq_count[f] : 0xFFFFFFFFu;
+  const uint16_t* sq = seq + (size_t)f * seq_stride;
+  uint8_t* lb = labels + (size_t)f * HW;
+  const unsigned lt = lanemask_lt();
+  int next_row = ((p_tile + W - 1) / W) * W;       // next pixel that starts an image row
+  int carry = -1;
+  unsigned ccnt = 0, flag = 0;
+#pragma unroll 2
+  for (int s = 0; s < kDTile / 32; ++s) {
+    const int p0 = p_tile + s * 32, p = p0 + (int)lane;
+    if (p0 >= HW) break;
+    const bool inb = p < HW;
+    const unsigned v = __shfl_sync(0xffffffffu, v_mine, s);
+    const unsigned idx = running + __popc(v >> (31 - lane));
+    running += __popc(v);
+    int label = 1;
+    if (inb) {
+      int l = 1;
+      if (idx < L) l = (int)__ldg(sq + idx); else flag |= 4u;     // sequence shorter than the contour map asks for
+      if (l >= K) { l = 1; flag |= 2u; }                          // label without a model row
+      label = l;
+      lb[p] = (uint8_t)label;
+    }
+    // per-label pixel counts of the tile (out-of-image lanes form a group of their own that is not counted)
+    {
+      const unsigned grp = __match_any_sync(0xffffffffu, inb ? label : 0x7fffffff);
+      if (inb && (grp & lt) == 0u) cnt[label] += (unsigned)__popc(grp);
+      __syncwarp();
+    }
+    // run count of the decoded map inside the tile, its first pixel excluded (extract_contour, cpp_modules.cpp:534-545)
+    {
+      int left = __shfl_up_sync(0xffffffffu, label, 1);
+      if (lane == 0) left = carry;
+      carry = __shfl_sync(0xffffffffu, label, 31);
+      bool rowstart = false;
+      if (W >= 32) {
+        if (next_row < p0 + 32) { rowstart = (p == next_row); next_row += W; }
+      } else {
+        rowstart = (p % W) == 0;
+      }
+      const bool c = inb && p != p_tile && (rowstart || label != left);
+      ccnt += __popc(__ballot_sync(0xffffffffu, c));
+    }
   }
-  warp_label_stats(label, inb, 1.0f, s_cnt, s_sum, s_flag);
-  tile_contour_count(label, inb, p, W, s_last, s_ccnt);  // run count of the decoded map (validation)
-  __syncthreads();
-  flush_tile_stats(K, f, tile, T, s_cnt, s_sum, s_flag, s_ccnt, bk);
+  flag = __reduce_or_sync(0xffffffffu, flag);
+  for (int l = lane; l < K; l += 32) {
+    const unsigned c = cnt[l];
+    bk.tile_hist[((size_t)f * T + tile) * K + l] = (uint16_t)c;
+    if (c) atomicAdd(&bk.label_cnt[(size_t)f * K + l], c);
+  }
+  if (lane == 0) {
+    bk.tile_ccnt[(size_t)f * T + tile] = (uint16_t)ccnt;
+    if (flag) atomicOr(&bk.flags[f], flag);
+  }
 }
 
-__global__ void __launch_bounds__(kDTile, 1)
+// The encoder's stable scatter run backwards: the warp's private counters start at tile_off (the position, in the frame's
+// label-major symbol stream, of the tile's first symbol of each label) and advance slice by slice; a pixel's symbol sits
+// at counter + (same-label lanes below it).  Then residual = f32((double)q * step), range = pred + residual, xyz = range * LUT.
+__global__ void __launch_bounds__(kDWarps * 32, 6)
 dequant_reconstruct_kernel(const uint8_t* __restrict__ labels, const int16_t* __restrict__ symbols, size_t sym_stride,
                            const uint32_t* __restrict__ sym_count, const float* __restrict__ model,
                            const double* __restrict__ steps, const float* __restrict__ lut, Book bk, int HW, int K, int T,
@@ -116,36 +155,58 @@ dequant_reconstruct_kernel(const uint8_t* __restrict__ labels, const int16_t* __
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* s_model = reinterpret_cast<float4*>(smem_raw);        // [K]
   double* s_step = reinterpret_cast<double*>(s_model + K);      // [K]
-  unsigned* s_tb = reinterpret_cast<unsigned*>(s_step + K);     // [K]
-  uint16_t* s_wcnt = reinterpret_cast<uint16_t*>(s_tb + K);     // [32][K]
-  const int f = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
-  for (int l = tid; l < K; l += kDTile) {
+  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_step + K);    // [kDWarps][K]
+  const int f = blockIdx.y, tid = threadIdx.x;
+  const unsigned lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x * kDWarps + (int)warp;
+  for (int l = tid; l < K; l += kDWarps * 32) {
     s_model[l] = reinterpret_cast<const float4*>(model)[(size_t)f * K + l];
     s_step[l] = steps[(size_t)f * K + l];
-    s_tb[l] = bk.tile_off[((size_t)f * T + tile) * K + l];
   }
-  const int p = tile * kDTile + tid;
-  const bool inb = p < HW;
-  const int label = inb ? labels[(size_t)f * HW + p] : 1;
-  const unsigned rank = tile_label_rank(label, K, s_wcnt);  // syncs cover the smem fills above
-  if (!inb) return;
-  float res = 0.0f;
-  if (label != 1) {
-    const unsigned pos = s_tb[label] + rank;
-    const unsigned n = sym_count ? sym_count[f] : 0xFFFFFFFFu;
-    const int q = pos < n ? (int)symbols[(size_t)f * sym_stride + pos] : 0;
-    res = (float)((double)q * s_step[label]);
-  }
-  const float4 m = s_model[label];
-  const float* t = lut + (size_t)p * 3;
-  float pred;
-  if (m.x + m.y + m.z == 0) pred = m.w;
-  else pred = -m.w / (m.x * t[0] + m.y * t[1] + m.z * t[2]);
-  const float rec = pred + res;
-  range_rec[(size_t)f * HW + p] = rec;
-  if (xyz) {
-    float* o = xyz + ((size_t)f * HW + p) * 3;
-    o[0] = rec * t[0]; o[1] = rec * t[1]; o[2] = rec * t[2];
+  unsigned* cnt = s_cnt + warp * K;
+  if (tile < T)
+    for (int l = lane; l < K; l += 32) cnt[l] = bk.tile_off[((size_t)f * T + tile) * K + l];
+  __syncthreads();
+  if (tile >= T) return;
+
+  const int p_tile = tile * kDTile;
+  const uint8_t* lb = labels + (size_t)f * HW;
+  const int16_t* sym = symbols + (size_t)f * sym_stride;
+  const unsigned n = sym_count ? sym_count[f] : 0xFFFFFFFFu;
+  float* rr = range_rec + (size_t)f * HW;
+  const unsigned lt = lanemask_lt();
+#pragma unroll 2
+  for (int s = 0; s < kDTile / 32; ++s) {
+    const int p0 = p_tile + s * 32, p = p0 + (int)lane;
+    if (p0 >= HW) break;
+    const bool inb = p < HW;
+    int label = inb ? (int)__ldg(lb + p) : 1;
+    if (label >= K) label = 1;                       // caller-supplied label maps: flagged by label_stats, decoded as empty
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    if (inb) { const float* t = lut + (size_t)p * 3; t0 = __ldg(t); t1 = __ldg(t + 1); t2 = __ldg(t + 2); }
+    const unsigned grp = __match_any_sync(0xffffffffu, label);
+    const unsigned base = cnt[label];                // same address for the whole group: one broadcast read
+    __syncwarp();
+    if ((grp & lt) == 0u) cnt[label] = base + (unsigned)__popc(grp);
+    __syncwarp();
+    float res = 0.0f;
+    if (label != 1) {
+      const unsigned pos = base + (unsigned)__popc(grp & lt);
+      const int q = pos < n ? (int)__ldg(sym + pos) : 0;
+      res = (float)((double)q * s_step[label]);      // utils/compress_utils.py:128-131
+    }
+    const float4 m = s_model[label];
+    float pred;
+    if (m.x + m.y + m.z == 0) pred = m.w;            // cpp_modules.cpp:271-279
+    else pred = -m.w / (m.x * t0 + m.y * t1 + m.z * t2);
+    const float rec = pred + res;
+    if (inb) {
+      rr[p] = rec;
+      if (xyz) {
+        float* o = xyz + ((size_t)f * HW + p) * 3;
+        o[0] = rec * t0; o[1] = rec * t1; o[2] = rec * t2;
+      }
+    }
   }
 }
 
@@ -176,8 +237,8 @@ extern "C" int rpcc_dequantize_batch(const uint8_t* labels, const int16_t* symbo
   // offsets (tile_off) + the counts a well-formed stream must have; no models are built on this path
   rc = rpcc_point_model_batch(nullptr, labels, nullptr, book, B, H, W, K, nullptr, results, stream);
   if (rc != RPCC_OK) return rc;
-  const size_t smem2 = (sizeof(float4) + sizeof(double) + sizeof(unsigned)) * K + sizeof(uint16_t) * 32 * (size_t)K + 16;
-  dequant_reconstruct_kernel<<<dim3(T, B), kDTile, smem2, st>>>(labels, symbols, sym_stride, sym_count, model, steps, lut,
+  const size_t smem2 = (sizeof(float4) + sizeof(double)) * K + sizeof(unsigned) * (size_t)kDWarps * K;
+  dequant_reconstruct_kernel<<<dim3((T + kDWarps - 1) / kDWarps, B), kDWarps * 32, smem2, st>>>(labels, symbols, sym_stride, sym_count, model, steps, lut,
                                                                 bk, HW, K, T, range_rec, xyz);
   RPCC_LAUNCH_CHECK("dequant_reconstruct_kernel");
   return RPCC_OK;
@@ -200,8 +261,8 @@ extern "C" int rpcc_decode_batch(const uint8_t* contour_bits, const uint16_t* se
   RPCC_CUDA(cudaMemsetAsync(bk.flags, 0, sizeof(unsigned) * (size_t)B, st));
   contour_prefix_kernel<<<B, 256, 0, st>>>(contour_bits, cbytes, HW, T, bk);
   RPCC_LAUNCH_CHECK("contour_prefix_kernel");
-  const size_t smem1 = (sizeof(unsigned long long) + sizeof(unsigned)) * K + sizeof(unsigned) * 66;
-  decode_labels_kernel<<<dim3(T, B), kDTile, smem1, st>>>(contour_bits, cbytes, seq, seq_stride, seq_count, HW, W, K, T,
+  const size_t smem1 = sizeof(unsigned) * (size_t)kDWarps * K;
+  decode_labels_kernel<<<dim3((T + kDWarps - 1) / kDWarps, B), kDWarps * 32, smem1, st>>>(contour_bits, cbytes, seq, seq_stride, seq_count, HW, W, K, T,
                                                           labels, bk);
   RPCC_LAUNCH_CHECK("decode_labels_kernel");
   return rpcc_dequantize_batch(labels, symbols, sym_stride, sym_count, model, steps, lut, B, H, W, K, range_rec, xyz, book,
