@@ -56,41 +56,56 @@ label_order_kernel(const uint8_t* __restrict__ labels, Book bk, int HW, int K, i
 }
 
 constexpr int kPlThreads = 128;
+constexpr int kPlWarps = kPlThreads / 32;
 constexpr int kPlMaxIter = 16;
 constexpr int kPlMaxSample = 16;
+constexpr int kPlCap = 2048;     // cluster pixels staged in shared memory (ray + range, 16 bytes each); larger clusters re-read them
 
-__device__ __forceinline__ double block_sum(double v, double* s_red) {   // all threads get the sum; fixed order
+// Sums over the CTA in a fixed order (xor tree inside a warp, warps in index order), so that a frame always gets the
+// same planes: the warp partials go to shared memory, the caller synchronises once and adds them up.
+__device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double t = 0.0;
-  for (int w = 0; w < kPlThreads / 32; ++w) t += s_red[w];
-  return t;
+  return v;
 }
 
-__global__ void __launch_bounds__(kPlThreads)
+// One CTA per (frame, cluster).  The cluster's pixels (a contiguous slice of `order`) are staged in shared memory once
+// -- unit ray and range, so that x = f32(range * ray) is formed exactly as PCTransformer.range_image_to_point_cloud
+// does -- and every later pass (hypothesis sampling, one scoring pass per hypothesis, the refit, the angle test) reads
+// them from there.  Registers stay low (one hypothesis at a time), so 7 CTAs share an SM.
+__global__ void __launch_bounds__(kPlThreads, 7)
 plane_model_kernel(const float* __restrict__ range, const float* __restrict__ lut, const unsigned* __restrict__ order,
-                   size_t order_stride, Book bk, int HW, int K, int min_pixels, float dist_thr, int ransac_n, int iters,
+                   size_t order_stride, Book bk, int HW, int K, int T, int min_pixels, float dist_thr, int ransac_n, int iters,
                    double cos_thr, unsigned long long seed, unsigned long long first_frame, float* __restrict__ model) {
+  extern __shared__ __align__(16) float4 s_pt[];     // [kPlCap] ray.x, ray.y, ray.z, range
   __shared__ double s_plane[kPlMaxIter][4];
-  __shared__ double s_red[kPlThreads / 32];
+  __shared__ double s_err[kPlMaxIter][kPlWarps];
+  __shared__ int s_inl[kPlMaxIter][kPlWarps];
+  __shared__ double s_part[10][kPlWarps];
   __shared__ double s_best[4];
   __shared__ int s_flag;
-  const int f = blockIdx.y, l = blockIdx.x + 2, tid = threadIdx.x;
+  const int f = blockIdx.y, l = blockIdx.x + 2, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (l >= K) return;
   const unsigned n = bk.label_cnt[(size_t)f * K + l];
   if ((int)n < min_pixels) return;              // utils/segment_utils.py:203-204: the point model stays
-  unsigned base = 0;
-  for (int q = 0; q < l; ++q) base += (q == 1) ? 0u : bk.label_cnt[(size_t)f * K + q];
+  // first symbol of the label in the frame's label-major stream = its offset in tile 0 (model.cu)
+  const unsigned base = bk.tile_off[(size_t)f * T * K + l];
   const unsigned* pix = order + (size_t)f * order_stride + base;
   const float* rg = range + (size_t)f * HW;
+  const bool staged = n <= (unsigned)kPlCap;
+  auto fetch = [&](unsigned k) {
+    const unsigned p = pix[k];
+    return make_float4(__ldg(lut + (size_t)p * 3), __ldg(lut + (size_t)p * 3 + 1), __ldg(lut + (size_t)p * 3 + 2), rg[p]);
+  };
+  if (staged)
+    for (unsigned k = tid; k < n; k += kPlThreads) s_pt[k] = fetch(k);
+  if (tid == 0) s_flag = 0;
+  __syncthreads();
+  auto ray = [&](unsigned k) { return staged ? s_pt[k] : fetch(k); };
   auto point = [&](unsigned k, double& x, double& y, double& z) {
     // PCTransformer.range_image_to_point_cloud (dataset/transformer.py:94-98): f32 products, then f64 (open3d)
-    const unsigned p = pix[k];
-    const float r = rg[p];
-    x = (double)(r * lut[(size_t)p * 3]); y = (double)(r * lut[(size_t)p * 3 + 1]); z = (double)(r * lut[(size_t)p * 3 + 2]);
+    const float4 v = ray(k);
+    x = (double)(v.w * v.x); y = (double)(v.w * v.y); z = (double)(v.w * v.z);
   };
 
   // ---- hypotheses: thread `it` draws ransac_n distinct points and fits their least-squares plane
@@ -121,26 +136,29 @@ plane_model_kernel(const float* __restrict__ range, const float* __restrict__ lu
   }
   __syncthreads();
 
-  // ---- score every hypothesis in one pass over the cluster
-  int inl[kPlMaxIter];
-  double err[kPlMaxIter];
-  for (int h = 0; h < kPlMaxIter; ++h) { inl[h] = 0; err[h] = 0.0; }
-  for (unsigned k = tid; k < n; k += kPlThreads) {
-    double x, y, z;
-    point(k, x, y, z);
-#pragma unroll
-    for (int h = 0; h < kPlMaxIter; ++h) {
-      if (h < iters) {
-        const double d = fabs(s_plane[h][0] * x + s_plane[h][1] * y + s_plane[h][2] * z + s_plane[h][3]);
-        if (d < (double)dist_thr) { ++inl[h]; err[h] += d * d; }
-      }
+  // ---- score the hypotheses, one pass over the staged cluster each
+  for (int h = 0; h < iters; ++h) {
+    const double p0 = s_plane[h][0], p1 = s_plane[h][1], p2 = s_plane[h][2], p3 = s_plane[h][3];
+    int inl = 0;
+    double err = 0.0;
+    for (unsigned k = tid; k < n; k += kPlThreads) {
+      double x, y, z;
+      point(k, x, y, z);
+      const double d = fabs(p0 * x + p1 * y + p2 * z + p3);
+      if (d < (double)dist_thr) { ++inl; err += d * d; }
     }
+    inl = __reduce_add_sync(0xffffffffu, inl);
+    err = warp_sum(err);
+    if (lane == 0) { s_inl[h][warp] = inl; s_err[h][warp] = err; }
   }
+  __syncthreads();
   int best = -1;
   double best_cnt = 0.0, best_rmse = 0.0;
-  for (int h = 0; h < iters; ++h) {
-    const double c = block_sum((double)inl[h], s_red);
-    const double e = block_sum(err[h], s_red);
+  for (int h = 0; h < iters; ++h) {              // every thread takes the same decision from the same numbers
+    int ci = 0;
+    double e = 0.0;
+    for (int w = 0; w < kPlWarps; ++w) { ci += s_inl[h][w]; e += s_err[h][w]; }
+    const double c = (double)ci;
     const bool valid = s_plane[h][0] != 0.0 || s_plane[h][1] != 0.0 || s_plane[h][2] != 0.0;
     if (!valid || c <= 0.0) continue;
     const double rmse = sqrt(e / c);
@@ -150,23 +168,35 @@ plane_model_kernel(const float* __restrict__ range, const float* __restrict__ lu
   if (best < 0) return;                          // no usable hypothesis: the point model stays (uniform decision)
 
   // ---- refit on the inliers of the best hypothesis
-  double s[10];
-  for (int q = 0; q < 10; ++q) s[q] = 0.0;
   const double b0 = s_plane[best][0], b1 = s_plane[best][1], b2 = s_plane[best][2], b3 = s_plane[best][3];
-  for (unsigned k = tid; k < n; k += kPlThreads) {
-    double x, y, z;
-    point(k, x, y, z);
-    if (fabs(b0 * x + b1 * y + b2 * z + b3) < (double)dist_thr) {
-      s[0] += 1.0; s[1] += x; s[2] += y; s[3] += z;
-      s[4] += x * x; s[5] += x * y; s[6] += x * z; s[7] += y * y; s[8] += y * z; s[9] += z * z;
+  {
+    double s[10];
+    for (int q = 0; q < 10; ++q) s[q] = 0.0;
+    for (unsigned k = tid; k < n; k += kPlThreads) {
+      double x, y, z;
+      point(k, x, y, z);
+      if (fabs(b0 * x + b1 * y + b2 * z + b3) < (double)dist_thr) {
+        s[0] += 1.0; s[1] += x; s[2] += y; s[3] += z;
+        s[4] += x * x; s[5] += x * y; s[6] += x * z; s[7] += y * y; s[8] += y * z; s[9] += z * z;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 10; ++q) {
+      const double v = warp_sum(s[q]);
+      if (lane == 0) s_part[q][warp] = v;
     }
   }
-  for (int q = 0; q < 10; ++q) s[q] = block_sum(s[q], s_red);
+  __syncthreads();
   if (tid == 0) {
+    double s[10];
+    for (int q = 0; q < 10; ++q) {
+      double t = 0.0;
+      for (int w = 0; w < kPlWarps; ++w) t += s_part[q][w];
+      s[q] = t;
+    }
     double pl[4];
     if (!plane_from_sums(s, pl)) { pl[0] = b0; pl[1] = b1; pl[2] = b2; pl[3] = b3; }
     for (int q = 0; q < 4; ++q) s_best[q] = pl[q];
-    s_flag = 0;
   }
   __syncthreads();
 
@@ -177,13 +207,14 @@ plane_model_kernel(const float* __restrict__ range, const float* __restrict__ lu
   const double nn = sqrt(a * a + b * b + c * c);
   int flag = 0;   // bit 0: some alpha above the threshold, bit 1: some alpha is NaN
   for (unsigned k = tid; k < n; k += kPlThreads) {
-    const unsigned p = pix[k];
-    const double sx = lut[(size_t)p * 3], sy = lut[(size_t)p * 3 + 1], sz = lut[(size_t)p * 3 + 2];
+    const float4 rv = ray(k);
+    const double sx = rv.x, sy = rv.y, sz = rv.z;
     const double v = fabs(a * sx + b * sy + c * sz) / nn * sqrt(sx * sx + sy * sy + sz * sz);
     if (!(v <= 1.0)) flag |= 2;               // arccos -> NaN (also v itself NaN)
     else if (v < cos_thr) flag |= 1;          // arccos(v) > threshold
   }
-  if (flag) atomicOr(&s_flag, flag);
+  flag = __reduce_or_sync(0xffffffffu, flag);
+  if (lane == 0 && flag) atomicOr(&s_flag, flag);
   __syncthreads();
   const bool keep = (s_flag & 2) || !(s_flag & 1);
   if (tid == 0 && keep) {
@@ -225,8 +256,8 @@ extern "C" int rpcc_plane_model_batch(const float* range, const float* lut, cons
   const int HW = H * W, T = (HW + RPCC_TILE - 1) / RPCC_TILE;
   const Book bk = make_book(book, B, T, K);
   const double cos_thr = cos(3.14159265358979323846 * ((double)angle_threshold_deg / 180.0));
-  plane_model_kernel<<<dim3(K - 2, B), kPlThreads, 0, as_stream(stream)>>>(
-      range, lut, order, order_stride, bk, HW, K, min_pixels, dist_thr, ransac_n, iterations, cos_thr,
+  plane_model_kernel<<<dim3(K - 2, B), kPlThreads, sizeof(float4) * kPlCap, as_stream(stream)>>>(
+      range, lut, order, order_stride, bk, HW, K, T, min_pixels, dist_thr, ransac_n, iterations, cos_thr,
       (unsigned long long)seed, (unsigned long long)first_frame, model);
   RPCC_LAUNCH_CHECK("plane_model_kernel");
   return RPCC_OK;

@@ -17,10 +17,12 @@ def dump(path):
         seeds = list(range(300, 324))
         pts, off, _ = synthetic.batch(seeds, lidar)
         d_pts, d_off = torch.from_numpy(pts).cuda(), torch.from_numpy(off).cuda()
-        with BatchEncoder(lidar, accuracy=0.02, max_batch=len(seeds)) as enc:
+        method = __import__("os").environ.get("AB_METHOD", "point")      # AB_METHOD=plane: per-cluster plane models too
+        with BatchEncoder(lidar, accuracy=0.02, max_batch=len(seeds), model_method=method) as enc:
             enc.encode_device(0, d_pts, d_off, len(seeds), None)
             enc.sync()
             out[lidar] = enc.device_buffer(0, "ground", (len(seeds), 4), torch.float32).cpu().numpy().copy()
+            out[lidar + "_model"] = enc.device_buffer(0, "model", (len(seeds), 102, 4), torch.float32).cpu().numpy().copy()
             sb = enc.device_buffer(0, "sym_base", (len(seeds) + 1,), torch.int64).cpu().numpy()
             out[lidar + "_sym"] = enc.device_buffer(0, "symbols", (int(sb[-1]),), torch.int16).cpu().numpy().copy()
     np.savez(path, **out)
