@@ -147,12 +147,17 @@ keypoints_kernel(const float* __restrict__ range, const uint8_t* __restrict__ la
   for (int j = warp; j < segments; j += kFeatThreads / 32) {
     unsigned long long* key = s_key + (size_t)j * N;
     // bitonic sort, ascending; padding keys (~0) end up past `per`
-    if (N == 32) warp_sort_regs<1>(key, lane);
-    else if (N == 64) warp_sort_regs<2>(key, lane);
-    else if (N == 128) warp_sort_regs<4>(key, lane);
-    else if (N == 256) warp_sort_regs<8>(key, lane);
-    else if (N == 512) warp_sort_regs<16>(key, lane);
-    else {
+    bool sort_small = false;   // (also: rows wider than 16384 pixels) the generic shared-memory network
+    // only the first `per` keys of the segment are real (the rest is ~0 padding up to the allocation N): sort the
+    // smallest power of two that holds them -- a row with few non-ground pixels sorts a fraction of N
+    if (N < 32) sort_small = true;
+    else if (per <= 32) warp_sort_regs<1>(key, lane);
+    else if (per <= 64) warp_sort_regs<2>(key, lane);
+    else if (per <= 128) warp_sort_regs<4>(key, lane);
+    else if (per <= 256) warp_sort_regs<8>(key, lane);
+    else if (per <= 512) warp_sort_regs<16>(key, lane);
+    else sort_small = true;
+    if (sort_small) {
       for (int k = 2; k <= N; k <<= 1) {
         for (int st = k >> 1; st > 0; st >>= 1) {
           for (int i = lane; i < N / 2; i += 32) {
