@@ -135,7 +135,10 @@ assign_labels_kernel(const float* __restrict__ range, const float* __restrict__ 
         dmin = fminf(dmin, d2[q]);                  // NaN centres drop out here and below (comparisons are false)
       }
       dmin = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(dmin)));
-      const float reach = sqrt_approx(dmin) * 1.00001f + 2.0f * R;
+      // a centre takes a pixel only with |p - c| < best_p (the pixel's ground residual), so it must also lie within
+      // max(best) + R of the sphere centre: slices of ground pixels (residuals of centimetres) keep no centre at all
+      const float maxb = __uint_as_float(__reduce_max_sync(0xffffffffu, valid ? __float_as_uint(best) : 0u));
+      const float reach = fminf(sqrt_approx(dmin) * 1.00001f + 2.0f * R, (maxb * 1.00001f + R) * 1.00001f);
       const float thr2 = reach * reach * 1.00001f;
       int bi = 0;
 #pragma unroll
