@@ -81,6 +81,24 @@ assign_labels_kernel(const float* __restrict__ range, const float* __restrict__ 
   int carry = -1;                                  // label left of the slice (none for the tile's first pixel)
   unsigned ccnt = 0, flag = 0;
 
+  // A centre at distance D from the ground plane cannot take a pixel whose ground residual is below D / 2: the residual
+  // |r - rplane| along the ray bounds the pixel's own distance to the plane, so |p - c| >= D - residual > residual.  With
+  // D the smallest such distance over the frame's centres (the FPS seeds lie beyond the ground threshold of it), a slice
+  // whose residuals all stay below D / 2 (minus a margin that covers the f32 rounding of both sides up to ranges of
+  // hundreds of metres) is ground without looking at any centre.
+  float skip_thr;
+  {
+    float dpl = __int_as_float(0x7f800000);
+#pragma unroll
+    for (int q = 0; q < MQ; ++q) {
+      const float4 c = s_c[q * 32 + lane];
+      if (q * 32 + lane < m) dpl = fminf(dpl, fabsf(torch_sum3(c.x * g0, c.y * g1, c.z * g2) + g3));
+    }
+    dpl = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(dpl)));
+    const float gn = sqrtf(g0 * g0 + g1 * g1 + g2 * g2);
+    skip_thr = 0.5f * (dpl / gn) * 0.99f - 2e-4f;       // NaN / inf planes: the comparison below is false, nothing is skipped
+    if (!(gn > 0.f) || !(dpl < 1e30f)) skip_thr = -1.f;
+  }
   // the loads of slice s + 1 are issued before slice s is worked on (the body is several hundred dependent instructions)
   float rn = 0.f, tn0 = 0.f, tn1 = 0.f, tn2 = 0.f;
   auto fetch = [&](int pp) {
@@ -114,7 +132,8 @@ assign_labels_kernel(const float* __restrict__ range, const float* __restrict__ 
       best = fabsf(r - rplane);                       // channel 0 (utils/segment_utils.py:143)
     }
     const bool valid = inb && r != 0.0f;
-    if (__any_sync(0xffffffffu, valid)) {
+    const float maxb = __uint_as_float(__reduce_max_sync(0xffffffffu, valid ? __float_as_uint(best) : 0u));
+    if (__any_sync(0xffffffffu, valid) && !(maxb < skip_thr)) {
       // bounding sphere of the slice's valid points: box centre, farthest valid point
       const int big = 0x7fffffff;
       const float ox = 0.5f * (ord2f(__reduce_min_sync(0xffffffffu, valid ? f2ord(x) : big)) + ord2f(__reduce_max_sync(0xffffffffu, valid ? f2ord(x) : -big)));
@@ -137,7 +156,6 @@ assign_labels_kernel(const float* __restrict__ range, const float* __restrict__ 
       dmin = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(dmin)));
       // a centre takes a pixel only with |p - c| < best_p (the pixel's ground residual), so it must also lie within
       // max(best) + R of the sphere centre: slices of ground pixels (residuals of centimetres) keep no centre at all
-      const float maxb = __uint_as_float(__reduce_max_sync(0xffffffffu, valid ? __float_as_uint(best) : 0u));
       const float reach = fminf(sqrt_approx(dmin) * 1.00001f + 2.0f * R, (maxb * 1.00001f + R) * 1.00001f);
       const float thr2 = reach * reach * 1.00001f;
       int bi = 0;
@@ -155,6 +173,8 @@ assign_labels_kernel(const float* __restrict__ range, const float* __restrict__ 
         }
       }
       if (valid) label = bi > 0 ? bi + 1 : 0;          // :168-169
+    } else if (valid) {
+      label = 0;                                       // every residual of the slice is below the skip threshold
     }
     if (inb) lb[p] = (uint8_t)label;
     // ---- per-label count and exact range sum (range * 2^28 as u64, see the header), private bins
