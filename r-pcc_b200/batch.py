@@ -38,6 +38,17 @@ def _pinned(shape, dtype):
     return torch.empty(shape, dtype=dtype, pin_memory=True)
 
 
+def default_workers():
+    """Host entropy-coder threads of one process: the box's cores split evenly over the ranks of a torchrun launch
+    (LOCAL_WORLD_SIZE), one left for the thread that feeds the GPU."""
+    n = os.cpu_count() or 2
+    try:
+        ranks = int(os.environ.get("LOCAL_WORLD_SIZE") or os.environ.get("WORLD_SIZE") or 1)
+    except ValueError:
+        ranks = 1
+    return max(1, n // max(ranks, 1) - 1)
+
+
 class BatchEncoder:
     """project -> ground fit -> FPS -> labels -> (key points) -> point (or plane) models -> quantise + pack for
     batches of frames.  `accuracy` is the yaml value (step = 2 * accuracy, tools/compress.py:46)."""
@@ -60,7 +71,7 @@ class BatchEncoder:
         self.max_points = int(max_points) if max_points else self.max_batch * 140000
         self.K = int(cfg["cluster_num"]) + 2
         self.method = basic_compressor or cfg["basic_compressor"]
-        self.workers = workers or max(1, (os.cpu_count() or 2) - 1)
+        self.workers = workers or default_workers()
         c = _EncoderConfig()
         c.H, c.W = self.lidar.H, self.lidar.W
         c.hfov, c.vmax, c.vmin = self.lidar.horizontal_FOV, self.lidar.vertical_max, self.lidar.vertical_min
@@ -239,7 +250,7 @@ class BatchDecoder:
         self.uniform = (cfg["compress_framework"] == "uniform") if nonuniform is None else (not nonuniform)
         self.method = basic_compressor or cfg["basic_compressor"]
         self.level_acc = np.array([self.step] * len(cfg["level_key_point_num"])) + np.array(cfg["level_delta_acc"])
-        self.workers = workers or max(1, (os.cpu_count() or 2) - 1)
+        self.workers = workers or default_workers()
         self._lut = None
 
     def _unpack(self, blob):
