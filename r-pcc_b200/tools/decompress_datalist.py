@@ -1,6 +1,7 @@
 """python -m rpcc_b200.tools.decompress_datalist --datalist L.txt --output_dir OUT --lidar Velodyne64E
 Batched mirror of the reference's tools/decompress_datalist.py:48-134; datalist lines are .rpcc files,
 outputs are .bin files under output_dir (the extension text replaced as the reference does, :129)."""
+import concurrent.futures as futures
 import os
 import time
 
@@ -23,12 +24,16 @@ def decompress(args):
     dec = BatchDecoder(args.lidar, accuracy=accuracy / 2, nonuniform=not uniform, compressor_cfg=dict(cfg),
                        basic_compressor=method, workers=args.workers)
     t0 = time.time()
+    pool = futures.ThreadPoolExecutor(max(1, args.workers))
     for b0 in range(0, len(mine), args.batch):
         names = mine[b0:b0 + args.batch]
-        blobs = [open(n, "rb").read() for n in names]
+        blobs = list(pool.map(lambda n: open(n, "rb").read(), names))
         out = dec.decode(blobs, want_xyz=True)
         xyz = out["xyz"].cpu().numpy()
-        for j, n in enumerate(names):
+
+        def save(j):
+            # dataset/dataset.py:72-81 (save_point_cloud_to_file): drop x + y + z == 0, append a zero intensity
+            n = names[j]
             fn = n[1:] if n[0] == "/" else n
             path = os.path.join(args.output_dir, fn)
             path = path.replace(path.split(".")[-1], "bin")
@@ -36,6 +41,9 @@ def decompress(args):
             pc = xyz[j].reshape(-1, 3)
             pc = pc[np.where(np.sum(pc, -1) != 0)]
             np.concatenate((pc, np.zeros((pc.shape[0], 1), np.float32)), -1).astype(np.float32).tofile(path)
+
+        list(pool.map(save, range(len(names))))     # numpy releases the GIL in these array passes
+    pool.shutdown()
     if rank == 0:
         dt = time.time() - t0
         print("Decompressed %d frames in %.2f s" % (len(mine), dt))
