@@ -224,7 +224,7 @@ class BatchEncoder:
 
     def _entropy(self, sections):
         bc = BasicCompressor(method_name=self.method, gzip_mtime=0)
-        return pack_bitstream({k: bc.compress(v) for k, v in sections.items()}, uniform=self.uniform)
+        return pack_bitstream({k: bc.compress(v, section=k) for k, v in sections.items()}, uniform=self.uniform)
 
     def compress(self, points, offsets, grounds=None):
         """-> list of B `.rpcc` byte strings (GPU stages + host entropy coding on the thread pool)."""

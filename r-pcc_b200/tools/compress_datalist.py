@@ -69,7 +69,7 @@ def compress(args):
     pending = []
 
     def entropy_and_save(i, sections, valid):
-        blob = pack_bitstream({k: bc.compress(v) for k, v in sections.items()}, uniform=uniform)
+        blob = pack_bitstream({k: bc.compress(v, section=k) for k, v in sections.items()}, uniform=uniform)
         out = output_path_for(args.output_dir, mine[i])
         os.makedirs(os.path.dirname(out), exist_ok=True)
         with open(out, "wb") as f:

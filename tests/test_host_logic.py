@@ -122,3 +122,23 @@ def test_output_path_rule_matches_reference_quirk():
     # str.replace of the extension text anywhere in the path (reference tools/compress_datalist.py:140)
     assert output_path_for("out", "/data/kitti/000001.bin") == "out/data/kitti/000001.rpcc"
     assert output_path_for("out", "/data/bin_files/000001.bin") == "out/data/rpcc_files/000001.rpcc"
+
+
+def test_bzip2_work_factor_does_not_change_the_bytes():
+    """The label-sequence section is sent to libbz2 with its own work factor (host entropy stage): the bytes
+    must be bz2.compress's -- on repetitive sequences long enough to take the tuned path, on short ones, on empty input."""
+    import bz2
+    from rpcc_b200.compress_utils import BasicCompressor
+    bc = BasicCompressor(method_name="bzip2")
+    rng = np.random.default_rng(7)
+    runs = np.repeat(rng.integers(0, 102, 6000), rng.integers(1, 4, 6000)).astype(np.uint16)
+    cases = [np.tile(np.array([0, 5, 0, 7], np.uint16), 20000), runs, np.tile(runs, 4), np.arange(3000, dtype=np.uint16),
+             np.zeros(0, np.uint16)]
+    for c in cases:
+        raw = c.tobytes()
+        assert bc.compress(raw, section="idx_sequence") == bz2.compress(raw)
+        assert bc.compress(c, section="idx_sequence") == bz2.compress(raw)
+        assert bc.compress(raw, section="residual_quantized") == bz2.compress(raw)
+        assert bc.compress(raw) == bz2.compress(raw)
+    assert BasicCompressor.bzip2_compress(cases[0].tobytes(), 1) == bz2.compress(cases[0].tobytes())
+    assert BasicCompressor.bzip2_compress(cases[0].tobytes(), 250) == bz2.compress(cases[0].tobytes())
