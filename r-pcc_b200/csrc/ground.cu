@@ -32,6 +32,12 @@ constexpr int kGfIters = 100;
 constexpr int kGfSample = 10;
 constexpr int kGfSlots = (kGfMaxPts + kGfThreads - 1) / kGfThreads;   // slots gathered per thread
 
+// point-plane distance of the scoring and refit passes (this kernel's own arithmetic, not the reference's: three fused
+// multiply-adds; both passes must use the same expression so that the refit sees the inliers that were counted)
+__device__ __forceinline__ float plane_dist(float a, float b, float c, float d, float x, float y, float z) {
+  return fabsf(__fmaf_rn(a, x, __fmaf_rn(b, y, __fmaf_rn(c, z, d))));
+}
+
 __global__ void __launch_bounds__(kGfThreads, RPCC_GF_OCC)
 ground_fit_kernel(const float* __restrict__ range, const float* __restrict__ lut, int HW, unsigned long long seed,
                   float z_below, float inlier_thr, float* __restrict__ ground) {
@@ -179,8 +185,8 @@ ground_fit_kernel(const float* __restrict__ range, const float* __restrict__ lut
         const float4 X = reinterpret_cast<const float4*>(px)[k4];
         const float4 Y = reinterpret_cast<const float4*>(py)[k4];
         const float4 Z = reinterpret_cast<const float4*>(pz)[k4];
-        const float d0 = fabsf(a * X.x + b * Y.x + c * Z.x + d), d1 = fabsf(a * X.y + b * Y.y + c * Z.y + d);
-        const float d2 = fabsf(a * X.z + b * Y.z + c * Z.z + d), d3 = fabsf(a * X.w + b * Y.w + c * Z.w + d);
+        const float d0 = plane_dist(a, b, c, d, X.x, Y.x, Z.x), d1 = plane_dist(a, b, c, d, X.y, Y.y, Z.y);
+        const float d2 = plane_dist(a, b, c, d, X.z, Y.z, Z.z), d3 = plane_dist(a, b, c, d, X.w, Y.w, Z.w);
         if (d0 < inlier_thr) { ++inl; err += d0 * d0; }
         if (d1 < inlier_thr) { ++inl; err += d1 * d1; }
         if (d2 < inlier_thr) { ++inl; err += d2 * d2; }
@@ -220,7 +226,7 @@ ground_fit_kernel(const float* __restrict__ range, const float* __restrict__ lut
     for (int q = 0; q < 10; ++q) s[q] = 0.0;
     for (int k = tid; k < ns; k += kGfThreads) {
       const double x = px[k], y = py[k], z = pz[k];
-      if (fabsf(a * px[k] + b * py[k] + c * pz[k] + d) < inlier_thr) {
+      if (plane_dist(a, b, c, d, px[k], py[k], pz[k]) < inlier_thr) {
         s[0] += 1.0; s[1] += x; s[2] += y; s[3] += z;
         s[4] += x * x; s[5] += x * y; s[6] += x * z; s[7] += y * y; s[8] += y * z; s[9] += z * z;
       }
