@@ -142,3 +142,18 @@ def test_bzip2_work_factor_does_not_change_the_bytes():
         assert bc.compress(raw) == bz2.compress(raw)
     assert BasicCompressor.bzip2_compress(cases[0].tobytes(), 1) == bz2.compress(cases[0].tobytes())
     assert BasicCompressor.bzip2_compress(cases[0].tobytes(), 250) == bz2.compress(cases[0].tobytes())
+
+
+def test_default_workers_split_the_cores_over_the_local_ranks(monkeypatch):
+    """Host entropy-coder threads: all cores but one for a single process, an even share under torchrun."""
+    from rpcc_b200 import batch
+    monkeypatch.setattr(os, "cpu_count", lambda: 32)
+    monkeypatch.delenv("LOCAL_WORLD_SIZE", raising=False)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    assert batch.default_workers() == 31
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    assert batch.default_workers() == 3
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "64")
+    assert batch.default_workers() == 1
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "junk")
+    assert batch.default_workers() == 31
