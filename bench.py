@@ -300,12 +300,14 @@ def main():
         d_tmp = torch.empty_like(d_pts[:h_pts.shape[0]])
         d_tmp.copy_(h_pts, non_blocking=True)
         torch.cuda.synchronize()
+        barrier()      # every rank probes its link at the same moment: under torchrun this is the contended figure
         l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0.record()
-        d_tmp.copy_(h_pts, non_blocking=True)
+        for _ in range(2):
+            d_tmp.copy_(h_pts, non_blocking=True)
         l1.record()
         torch.cuda.synchronize()
-        link_gbs = h_pts.numel() * 4 / (l0.elapsed_time(l1) / 1000.0) / 1e9
+        link_gbs = 2 * h_pts.numel() * 4 / (l0.elapsed_time(l1) / 1000.0) / 1e9
         del d_tmp
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
