@@ -115,6 +115,16 @@ def fps(points, m, fma_mode=0):
     return idx
 
 
+def ground_fit(range_image, lut, seed=0x5EED, frame=0, threads=512):
+    """The PRODUCT's deterministic ground RANSAC restated (rpcc_oracle.c: orc_ground_fit) -- open3d's segment_plane,
+    which the reference calls on an unseeded subsample (utils/segment_utils.py:74-82,101-108), cannot be pinned."""
+    ri = _f32(range_image).reshape(-1)
+    lut = _f32(lut)
+    g = np.empty(4, np.float32)
+    lib().orc_ground_fit(_p(ri), _p(lut), C.c_int64(ri.size), C.c_uint64(seed), C.c_uint64(frame), int(threads), _p(g))
+    return g
+
+
 def nonground_points(xyz, ground_model, thr=0.1, assoc=0):
     xyz = _f32(xyz)
     g = _f32(ground_model)

@@ -526,3 +526,151 @@ ORC_API void orc_chamfer_nn(const float* a, int64_t n, const float* b, int64_t m
     dist[i] = best; idx[i] = bi;
   }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Ground plane: restatement of the PRODUCT's deterministic RANSAC (r-pcc_b200/csrc/ground.cu), not of
+ * the reference -- utils/segment_utils.py:74-82,101-108 hands an unseeded random subsample to open3d's
+ * segment_plane, which is third-party, absent and randomised ("parity unpinned").  What the reference
+ * fixes is kept (candidates z < -1.5, at most 5000 of them, fewer than 800 -> every pixel, 10-point
+ * least-squares hypotheses, 100 of them, inliers at 0.1 m, refit on the winner's inliers); this function
+ * repeats the device's counter-based samples and its summation orders so that the fitted plane can be
+ * compared bit for bit (a regression pin for the kernel; tests/test_gpu_stages.py).
+ * `threads` = threads per CTA of ground_fit_kernel (512): it fixes the order of the refit's partial sums. */
+static uint64_t orc_splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+/* open3d GetPlaneFromPoints from the ten moments (ransac.cuh: plane_from_sums) */
+static int orc_plane_from_sums(const double* s, double* plane) {
+  const double n = s[0];
+  if (n < 3.0) return 0;
+  const double cx = s[1] / n, cy = s[2] / n, cz = s[3] / n;
+  const double xx = s[4] - n * cx * cx, xy = s[5] - n * cx * cy, xz = s[6] - n * cx * cz;
+  const double yy = s[7] - n * cy * cy, yz = s[8] - n * cy * cz, zz = s[9] - n * cz * cz;
+  const double dx = yy * zz - yz * yz, dy = xx * zz - xz * xz, dz = xx * yy - xy * xy;
+  const double dmax = fmax(dx, fmax(dy, dz));
+  if (!(dmax > 0.0)) return 0;
+  double a, b, c;
+  if (dmax == dx) { a = dx; b = xz * yz - xy * zz; c = xy * yz - xz * yy; }
+  else if (dmax == dy) { a = xz * yz - xy * zz; b = dy; c = xy * xz - yz * xx; }
+  else { a = xy * yz - xz * yy; b = xy * xz - yz * xx; c = dz; }
+  const double nn = sqrt(a * a + b * b + c * c);
+  if (!(nn > 0.0)) return 0;
+  a /= nn; b /= nn; c /= nn;
+  plane[0] = a; plane[1] = b; plane[2] = c; plane[3] = -(a * cx + b * cy + c * cz);
+  return 1;
+}
+
+static inline float orc_plane_dist(float a, float b, float c, float d, float x, float y, float z) {
+  return fabsf(fmaf(a, x, fmaf(b, y, fmaf(c, z, d))));
+}
+
+ORC_API void orc_ground_fit(const float* range, const float* lut, int64_t hw, uint64_t seed, uint64_t frame,
+                            int threads, float* ground) {
+  enum { kMax = 5000, kIters = 100, kSample = 10 };
+  const float z_below = -1.5f, thr = 0.1f;
+  /* candidates in raster order */
+  int64_t nc = 0;
+  for (int64_t p = 0; p < hw; ++p) nc += (range[p] * lut[3 * p + 2] < z_below);
+  const int use_all = nc < 800;
+  if (use_all) nc = hw;
+  const int ns = (int)(nc < kMax ? nc : kMax);
+  float* px = (float*)malloc(sizeof(float) * 3 * (size_t)ns);
+  float *py = px + ns, *pz = py + ns;
+  {
+    int64_t r = -1, p = -1;                 /* candidate number of pixel p */
+    for (int s = 0; s < ns; ++s) {
+      const int64_t want = (ns != nc) ? (int64_t)(((uint32_t)s * (uint32_t)nc + (uint32_t)ns - 1u) / (uint32_t)ns) : s;
+      while (r < want) { ++p; if (use_all || range[p] * lut[3 * p + 2] < z_below) ++r; }
+      const float rr = range[p];
+      px[s] = rr * lut[3 * p]; py[s] = rr * lut[3 * p + 1]; pz[s] = rr * lut[3 * p + 2];
+    }
+  }
+  const int ns4 = (ns + 3) >> 2;
+  double planes[kIters][4];
+  uint64_t best = 0;
+  for (int it = 0; it < kIters; ++it) {
+    uint64_t st = orc_splitmix64(orc_splitmix64(seed + frame) ^ ((uint64_t)it << 40));
+    double s[10] = {0};
+    for (int j = 0; j < kSample; ++j) {
+      st = orc_splitmix64(st);              /* lane j walks j + 1 links of the one chain */
+      const int k = (int)(st % (uint64_t)ns);
+      const double x = px[k], y = py[k], z = pz[k];
+      s[0] += 1.0; s[1] += x; s[2] += y; s[3] += z;
+      s[4] += x * x; s[5] += x * y; s[6] += x * z; s[7] += y * y; s[8] += y * z; s[9] += z * z;
+    }
+    double pl[4] = {0, 0, 0, 0};
+    if (!orc_plane_from_sums(s, pl)) { pl[0] = pl[1] = pl[2] = pl[3] = 0.0; }
+    for (int q = 0; q < 4; ++q) planes[it][q] = pl[q];
+    const float a = (float)pl[0], b = (float)pl[1], c = (float)pl[2], d = (float)pl[3];
+    int inl_l[32];
+    float err_l[32];
+    for (int L = 0; L < 32; ++L) { inl_l[L] = 0; err_l[L] = 0.f; }
+    if (a != 0.f || b != 0.f || c != 0.f) {
+      for (int L = 0; L < 32; ++L)
+        for (int k4 = L; k4 < ns4; k4 += 32)
+          for (int e = 0; e < 4; ++e) {
+            const int k = 4 * k4 + e;
+            if (k >= ns) continue;          /* the device pads with NaN: never an inlier */
+            const float dd = orc_plane_dist(a, b, c, d, px[k], py[k], pz[k]);
+            if (dd < thr) { ++inl_l[L]; err_l[L] += dd * dd; }
+          }
+    }
+    for (int o = 16; o > 0; o >>= 1) {      /* the warp's xor tree */
+      int ni[32];
+      float ne[32];
+      for (int L = 0; L < 32; ++L) { ni[L] = inl_l[L] + inl_l[L ^ o]; ne[L] = err_l[L] + err_l[L ^ o]; }
+      memcpy(inl_l, ni, sizeof ni);
+      memcpy(err_l, ne, sizeof ne);
+    }
+    const int inl = inl_l[0];
+    const float rmse = inl > 0 ? sqrtf(err_l[0] / (float)inl) : 1e9f;
+    const float scaled = rmse * 1e6f;
+    const uint32_t qr = scaled >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)scaled;    /* cvt.rzi.u32.f32 saturates */
+    const uint32_t qc = qr < 0xFFFFFFu ? qr : 0xFFFFFFu;
+    const uint64_t score = ((uint64_t)inl << 40) | ((uint64_t)(0xFFFFFFu - qc) << 8) | (uint64_t)(0xFFu - it);
+    if (score > best) best = score;
+  }
+  const int bi = 0xFF - (int)(best & 0xFFull);
+  const double* sb = planes[bi];
+  /* refit: thread t adds its points k = t, t + threads, ... ; xor tree inside each warp; warps in index order */
+  double sums[10];
+  {
+    const float a = (float)sb[0], b = (float)sb[1], c = (float)sb[2], d = (float)sb[3];
+    const int nw = threads / 32;
+    double* part = (double*)calloc((size_t)threads * 10, sizeof(double));
+    for (int t = 0; t < threads; ++t)
+      for (int k = t; k < ns; k += threads) {
+        const double x = px[k], y = py[k], z = pz[k];
+        if (orc_plane_dist(a, b, c, d, px[k], py[k], pz[k]) < thr) {
+          double* s = part + (size_t)t * 10;
+          s[0] += 1.0; s[1] += x; s[2] += y; s[3] += z;
+          s[4] += x * x; s[5] += x * y; s[6] += x * z; s[7] += y * y; s[8] += y * z; s[9] += z * z;
+        }
+      }
+    for (int q = 0; q < 10; ++q) {
+      double total = 0.0;
+      for (int w = 0; w < nw; ++w) {
+        double v[32], nv[32];
+        for (int L = 0; L < 32; ++L) v[L] = part[(size_t)(w * 32 + L) * 10 + q];
+        for (int o = 16; o > 0; o >>= 1) {
+          for (int L = 0; L < 32; ++L) nv[L] = v[L] + v[L ^ o];
+          memcpy(v, nv, sizeof v);
+        }
+        total += v[0];
+      }
+      sums[q] = total;
+    }
+    free(part);
+  }
+  double pl[4];
+  if (!orc_plane_from_sums(sums, pl)) {
+    if (sb[0] != 0.0 || sb[1] != 0.0 || sb[2] != 0.0) { for (int q = 0; q < 4; ++q) pl[q] = sb[q]; }
+    else { pl[0] = 0.0; pl[1] = 0.0; pl[2] = 1.0; pl[3] = 1.73; }
+  }
+  for (int q = 0; q < 4; ++q) ground[q] = (float)pl[q];
+  free(px);
+}

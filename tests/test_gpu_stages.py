@@ -272,3 +272,39 @@ def test_model_quantize_pack(T, R, lidar):
         assert symbols[b, :nsym].cpu().numpy().tobytes() == sec["residual_quantized"]
         assert contour[b].cpu().numpy().tobytes() == sec["contour_map"]
         assert seq[b, :nseq].cpu().numpy().tobytes() == sec["idx_sequence"]
+
+
+# ----------------------------------------------------------------------------- ground plane (the product's own RANSAC)
+@pytest.mark.parametrize("lidar", LIDARS)
+def test_ground_fit_matches_its_restatement(T, R, lidar):
+    """open3d's segment_plane cannot be pinned (absent, and the reference feeds it an unseeded subsample), so the
+    ground plane is the product's own deterministic RANSAC; the oracle restates it (same counter-based samples, same
+    summation orders) and the device planes must equal it bit for bit -- single-frame op and batched kernel (frame
+    keys), plus the reference's fallback when fewer than 800 pixels lie below -1.5 m (every pixel is a candidate)."""
+    from rpcc_b200.segment_utils import PointCloudSegment
+    seeds = [81, 82, 83, 84, 85]
+    pts, off, _ = _frames(R, lidar, seeds)
+    cfg, rng = _project_dev(T, R, pts, off, lidar)
+    lut = cfg.transform_map()
+    seg = PointCloudSegment(lut)
+    ris = rng.cpu().numpy().reshape(len(seeds), cfg.H, cfg.W)
+    for b in range(len(seeds)):
+        for seed in (0x5EED, 7):
+            got = seg.ransac_plane_segmentation(ris[b], seed=seed)
+            want = oracle.ground_fit(ris[b], lut, seed=seed, frame=0)
+            assert got.tobytes() == want.tobytes(), (lidar, b, seed, got, want)
+    # batched kernel: frame b of the launch is keyed seed + b
+    import ctypes as C
+    from rpcc_b200 import _lib
+    from rpcc_b200._lib import check, ptr
+    d_lut = T.from_numpy(lut).cuda()
+    d_g = T.empty((len(seeds), 4), dtype=T.float32, device="cuda")
+    check(_lib.lib().rpcc_ground_fit_batch(ptr(rng), ptr(d_lut), len(seeds), cfg.H, cfg.W, C.c_uint64(0x5EED), ptr(d_g),
+                                           C.c_void_p(T.cuda.current_stream().cuda_stream)))
+    T.cuda.synchronize()
+    got = d_g.cpu().numpy()
+    for b in range(len(seeds)):
+        assert got[b].tobytes() == oracle.ground_fit(ris[b], lut, seed=0x5EED, frame=b).tobytes(), (lidar, b)
+    # no ground below the sensor: fewer than 800 candidates -> all pixels (utils/segment_utils.py:105-106)
+    bare = np.where(ris[0] * lut[..., 2] < -1.5, 0.0, ris[0]).astype(np.float32)
+    assert seg.ransac_plane_segmentation(bare).tobytes() == oracle.ground_fit(bare, lut).tobytes()
