@@ -216,6 +216,28 @@ def test_long_launch_every_cta_takes_several_frames(R, lidar, nonuniform, B):
         assert np.isfinite(g1).all() and (np.abs(np.linalg.norm(g1[:, :3], axis=1) - 1.0) < 1e-4).all()
 
 
+@pytest.mark.parametrize("lidar", ["Velodyne64E", "VelodyneVLP16"])
+def test_encoder_with_device_ground_is_byte_exact_against_the_oracle(R, lidar):
+    """No ground model injected anywhere: the device fits the plane (keyed by the frame's index within the call, across
+    the pipeline stages of encode_host) and the oracle fits its restatement of the same RANSAC -- every section of
+    every frame must still come out byte for byte."""
+    from rpcc_b200 import synthetic
+    from rpcc_b200.batch import BatchEncoder
+    seeds = list(range(90, 97))
+    pts, off, _ = synthetic.batch(seeds, lidar)
+    H, W, hf, vmax, vmin = oracle.lidar_params(lidar)
+    lut = oracle.transform_map(H, W, hf, vmax, vmin)
+    with BatchEncoder(lidar, accuracy=0.02, max_batch=3, host_chunk=3) as enc:
+        out = enc.encode_host(pts, off, None)
+        for b in range(len(seeds)):
+            p = pts[off[b]:off[b + 1]]
+            g = oracle.ground_fit(oracle.project(p, H, W, hf, vmax, vmin), lut, seed=0x5EED, frame=b)
+            want = oracle.compress_frame(p, lidar, g)["sections"]
+            got = BatchEncoder.frame_sections(out, b)
+            for k, v in want.items():
+                assert got[k] == v, (lidar, b, k)
+
+
 def test_encoder_device_path_and_ground_fit(R):
     """Device-resident inputs, ground fitted on the device: deterministic, close to the true plane, and the
     rest of the chain is byte-exact against the oracle GIVEN that fitted plane."""
