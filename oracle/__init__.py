@@ -167,6 +167,22 @@ def model_param_point(range_image, seg, ground_model):
     return mp.astype(np.float32)
 
 
+PLANE_SEED = 0x5EED ^ 0x9E3779B97F4A7C15      # the encoder's key for the per-cluster planes (csrc/encoder.cu)
+
+
+def plane_models_device(range_image, lut, seg, model_point, seed=PLANE_SEED, frame=0, angle_threshold=75.0,
+                        min_pixels=30, dist_thr=0.1, ransac_n=4, iters=10, threads=128):
+    """The PRODUCT's deterministic per-cluster RANSAC restated (rpcc_oracle.c: orc_plane_models): the point-model rows
+    `model_point` (K,4) with the rows of the accepted planes replaced.  (oracle.plane restates the REFERENCE's branch
+    with a seeded stand-in for open3d instead.)"""
+    ri = _f32(range_image).reshape(-1)
+    mp = _f32(model_point).copy()
+    lib().orc_plane_models(_p(ri), _p(_f32(lut)), _p(_i32(seg)), C.c_int64(ri.size), int(mp.shape[0]), C.c_uint64(seed),
+                           C.c_uint64(frame), int(min_pixels), C.c_float(dist_thr), int(ransac_n), int(iters),
+                           C.c_float(angle_threshold), int(threads), _p(mp))
+    return mp
+
+
 def intra_predict(seg, model_param, lut):
     seg = _i32(seg)
     mp = _f32(model_param)
@@ -285,7 +301,7 @@ def write_rpcc(sections, method="bzip2"):
 
 def compress_frame(points, lidar="Velodyne64E", ground_model=None, accuracy=0.02, nonuniform=False,
                    cluster_num=100, assoc=0, fma_mode=0, cfg=None, model_method="point", plane_seed=0,
-                   angle_threshold=75):
+                   angle_threshold=75, plane_impl="reference", frame=0):
     """tools/compress.py:44-133 given the ground model; returns a dict of every intermediate (the parity
     tests compare the CUDA path stage by stage).  model_method='plane' uses oracle.plane (open3d stand-in)."""
     H, W, hfov, vmax, vmin = lidar_params(lidar)
@@ -293,7 +309,10 @@ def compress_frame(points, lidar="Velodyne64E", ground_model=None, accuracy=0.02
     step = accuracy * 2
     ri = project(points, H, W, hfov, vmax, vmin)
     seg, cidx, centers = segment(ri, lut, ground_model, cluster_num, 0.1, assoc, fma_mode)
-    if model_method == "plane":
+    if model_method == "plane" and plane_impl == "device":
+        mp = plane_models_device(ri, lut, seg, model_param_point(ri, seg, ground_model), frame=frame,
+                                 angle_threshold=float(angle_threshold))
+    elif model_method == "plane":
         from . import plane as _plane
         cm = _plane.cluster_modeling_plane(lut, ri, seg, angle_threshold, plane_seed)
         mp = np.concatenate((np.asarray(ground_model, np.float64).reshape(1, 4), cm), 0).astype(np.float32)

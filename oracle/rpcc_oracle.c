@@ -674,3 +674,130 @@ ORC_API void orc_ground_fit(const float* range, const float* lut, int64_t hw, ui
   for (int q = 0; q < 4; ++q) ground[q] = (float)pl[q];
   free(px);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-cluster plane models: restatement of the PRODUCT's deterministic RANSAC
+ * (r-pcc_b200/csrc/plane.cu: plane_model_kernel), for the same reason as orc_ground_fit -- the
+ * reference's cluster_modeling(model_method='plane') (utils/segment_utils.py:188-216) calls open3d's
+ * randomised segment_plane per cluster.  Kept from the reference: clusters under 30 pixels stay point
+ * models, 4-point least-squares hypotheses, 10 of them, inliers at 0.1 m by count then rmse, refit on
+ * the winner's inliers, plane_angle_validation (:84-93) with its precedence quirk and numpy's NaN
+ * semantics.  `model` holds the point-model rows on entry ([K][4] f32); rows of accepted planes are
+ * overwritten.  `threads` = threads per CTA of plane_model_kernel (128): it fixes the summation order. */
+ORC_API void orc_plane_models(const float* range, const float* lut, const int32_t* seg, int64_t hw, int K,
+                              uint64_t seed, uint64_t frame, int min_pixels, float dist_thr, int ransac_n,
+                              int iters, float angle_threshold_deg, int threads, float* model) {
+  const double thr = (double)dist_thr;
+  const double cos_thr = cos(3.14159265358979323846 * ((double)angle_threshold_deg / 180.0));
+  const int nw = threads / 32;
+  int64_t* pix = (int64_t*)malloc(sizeof(int64_t) * (size_t)hw);
+  double* part = (double*)malloc(sizeof(double) * (size_t)threads * 10);
+  for (int l = 2; l < K; ++l) {
+    int64_t n = 0;
+    for (int64_t p = 0; p < hw; ++p) if (seg[p] == l) pix[n++] = p;      /* raster order inside the label */
+    if (n < min_pixels) continue;
+#define ORC_PT(k, x, y, z) do { const int64_t p_ = pix[k]; const float r_ = range[p_];                      \
+      (x) = (double)(r_ * lut[3 * p_]); (y) = (double)(r_ * lut[3 * p_ + 1]); (z) = (double)(r_ * lut[3 * p_ + 2]); } while (0)
+    double planes[16][4];
+    for (int it = 0; it < iters; ++it) {
+      uint64_t st = orc_splitmix64(orc_splitmix64(seed + frame) ^ ((uint64_t)l << 48) ^ ((uint64_t)it << 32));
+      uint32_t pick[16];
+      double s[10] = {0};
+      for (int j = 0; j < ransac_n; ++j) {
+        uint32_t k;
+        int dup;
+        do {
+          st = orc_splitmix64(st);
+          k = (uint32_t)(st % (uint64_t)n);
+          dup = 0;
+          for (int e = 0; e < j; ++e) dup = dup || (pick[e] == k);
+        } while (dup);
+        pick[j] = k;
+        double x, y, z;
+        ORC_PT(k, x, y, z);
+        s[0] += 1.0; s[1] += x; s[2] += y; s[3] += z;
+        s[4] += x * x; s[5] += x * y; s[6] += x * z; s[7] += y * y; s[8] += y * z; s[9] += z * z;
+      }
+      double pl[4] = {0, 0, 0, 0};
+      if (!orc_plane_from_sums(s, pl)) { pl[0] = pl[1] = pl[2] = pl[3] = 0.0; }
+      for (int q = 0; q < 4; ++q) planes[it][q] = pl[q];
+    }
+    /* scores: thread t adds k = t, t + threads, ...; xor tree inside a warp; warps in index order */
+    int best = -1;
+    double best_cnt = 0.0, best_rmse = 0.0;
+    for (int h = 0; h < iters; ++h) {
+      const double p0 = planes[h][0], p1 = planes[h][1], p2 = planes[h][2], p3 = planes[h][3];
+      int ci = 0;
+      double e = 0.0;
+      for (int w = 0; w < nw; ++w) {
+        double v[32], nv[32];
+        for (int L = 0; L < 32; ++L) {
+          double err = 0.0;
+          for (int64_t k = w * 32 + L; k < n; k += threads) {
+            double x, y, z;
+            ORC_PT(k, x, y, z);
+            const double d = fabs(p0 * x + p1 * y + p2 * z + p3);
+            if (d < thr) { ++ci; err += d * d; }
+          }
+          v[L] = err;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          for (int L = 0; L < 32; ++L) nv[L] = v[L] + v[L ^ o];
+          memcpy(v, nv, sizeof v);
+        }
+        e += v[0];
+      }
+      const double c = (double)ci;
+      const int valid = p0 != 0.0 || p1 != 0.0 || p2 != 0.0;
+      if (!valid || c <= 0.0) continue;
+      const double rmse = sqrt(e / c);
+      if (best < 0 || c > best_cnt || (c == best_cnt && rmse < best_rmse)) { best = h; best_cnt = c; best_rmse = rmse; }
+    }
+    if (best < 0) continue;
+    const double b0 = planes[best][0], b1 = planes[best][1], b2 = planes[best][2], b3 = planes[best][3];
+    memset(part, 0, sizeof(double) * (size_t)threads * 10);
+    for (int t = 0; t < threads; ++t)
+      for (int64_t k = t; k < n; k += threads) {
+        double x, y, z;
+        ORC_PT(k, x, y, z);
+        if (fabs(b0 * x + b1 * y + b2 * z + b3) < thr) {
+          double* s = part + (size_t)t * 10;
+          s[0] += 1.0; s[1] += x; s[2] += y; s[3] += z;
+          s[4] += x * x; s[5] += x * y; s[6] += x * z; s[7] += y * y; s[8] += y * z; s[9] += z * z;
+        }
+      }
+    double sums[10];
+    for (int q = 0; q < 10; ++q) {
+      double total = 0.0;
+      for (int w = 0; w < nw; ++w) {
+        double v[32], nv[32];
+        for (int L = 0; L < 32; ++L) v[L] = part[(size_t)(w * 32 + L) * 10 + q];
+        for (int o = 16; o > 0; o >>= 1) {
+          for (int L = 0; L < 32; ++L) nv[L] = v[L] + v[L ^ o];
+          memcpy(v, nv, sizeof v);
+        }
+        total += v[0];
+      }
+      sums[q] = total;
+    }
+    double pl[4];
+    if (!orc_plane_from_sums(sums, pl)) { pl[0] = b0; pl[1] = b1; pl[2] = b2; pl[3] = b3; }
+    /* plane_angle_validation, f64 like numpy: arccos(|n.s| / |n| * |s|) */
+    const double a = pl[0], b = pl[1], c = pl[2], d = pl[3];
+    const double nn = sqrt(a * a + b * b + c * c);
+    int flag = 0;
+    for (int64_t k = 0; k < n; ++k) {
+      const int64_t p = pix[k];
+      const double sx = lut[3 * p], sy = lut[3 * p + 1], sz = lut[3 * p + 2];
+      const double v = fabs(a * sx + b * sy + c * sz) / nn * sqrt(sx * sx + sy * sy + sz * sz);
+      if (!(v <= 1.0)) flag |= 2;
+      else if (v < cos_thr) flag |= 1;
+    }
+    if ((flag & 2) || !(flag & 1)) {
+      model[4 * l] = (float)a; model[4 * l + 1] = (float)b; model[4 * l + 2] = (float)c; model[4 * l + 3] = (float)d;
+    }
+#undef ORC_PT
+  }
+  free(part);
+  free(pix);
+}

@@ -106,3 +106,28 @@ def test_cluster_modeling_plane_mirror(example_points):
         pred = oracle.intra_predict(seg, np.concatenate((g, rows), 0), lut)
         e.append(float(np.abs((ri - pred)[ri > 0]).mean()))
     assert e[0] <= 1.05 * e[1], e
+
+
+@pytest.mark.parametrize("accuracy", [0.01, 0.05])
+def test_plane_models_match_their_restatement_byte_for_byte(frames, accuracy):
+    """open3d's per-cluster segment_plane cannot be pinned; the product's own deterministic RANSAC can: the oracle
+    restates it (orc_plane_models: same counter-based samples keyed by frame and label, same summation orders), so the
+    model rows and with them every section of the .rpcc stream must be byte-exact -- with the ground injected and with
+    the ground fitted on the device."""
+    from rpcc_b200.batch import BatchEncoder
+    pts, off, grounds = frames
+    B = len(SEEDS)
+    H, W, hf, vmax, vmin = oracle.lidar_params("Velodyne64E")
+    lut = oracle.transform_map(H, W, hf, vmax, vmin)
+    with BatchEncoder("Velodyne64E", accuracy=accuracy, max_batch=3, host_chunk=3, model_method="plane") as enc:
+        for inject in (True, False):
+            out = enc.encode_host(pts, off, grounds if inject else None)
+            for b in range(B):
+                p = pts[off[b]:off[b + 1]]
+                g = grounds[b] if inject else oracle.ground_fit(oracle.project(p, H, W, hf, vmax, vmin), lut, frame=b)
+                want = oracle.compress_frame(p, "Velodyne64E", g, accuracy=accuracy, model_method="plane",
+                                             plane_impl="device", frame=b)
+                got = BatchEncoder.frame_sections(out, b)
+                assert got["plane_param"] == want["sections"]["plane_param"], (accuracy, inject, b)
+                for k, v in want["sections"].items():
+                    assert got[k] == v, (accuracy, inject, b, k)
