@@ -173,3 +173,34 @@ def test_plane_oracle_restatement_properties():
     q[:, 2] = 0.25 * q[:, 0] - 0.5 * q[:, 1] + 3.0
     pl = oplane.get_plane_from_points(q)
     assert np.abs(q @ pl[:3] + pl[3]).max() < 1e-9 and abs(np.linalg.norm(pl[:3]) - 1) < 1e-12
+
+
+def test_oracle_ransac_restatements_behave():
+    """orc_ground_fit / orc_plane_models restate the PRODUCT's deterministic RANSACs (open3d cannot be pinned): on the
+    CPU they are checked by what the codec guarantees -- a unit ground normal near the synthetic scene's true plane,
+    reproducible, keyed by seed and frame; plane-model rows that are unit normals or point rows, a smaller stream than
+    with point models and the error bound of the codec after decoding."""
+    from rpcc_b200 import synthetic
+    pts, g_true = synthetic.frame(77, "Velodyne64E")
+    H, W, hf, vmax, vmin = oracle.lidar_params("Velodyne64E")
+    lut = oracle.transform_map(H, W, hf, vmax, vmin)
+    ri = oracle.project(pts, H, W, hf, vmax, vmin)
+    g = oracle.ground_fit(ri, lut)
+    assert abs(float(np.linalg.norm(g[:3])) - 1.0) < 1e-5
+    t = np.asarray(g_true, np.float64) * np.sign(g_true[2]) * np.sign(g[2])
+    assert float(np.abs(g[:3] - t[:3]).max()) < 0.02 and abs(float(g[3] - t[3])) < 0.1
+    assert oracle.ground_fit(ri, lut).tobytes() == g.tobytes()
+    assert oracle.ground_fit(ri, lut, frame=1).tobytes() != g.tobytes() or oracle.ground_fit(ri, lut, seed=9).tobytes() != g.tobytes()
+    point = oracle.compress_frame(pts, "Velodyne64E", g)
+    plane = oracle.compress_frame(pts, "Velodyne64E", g, model_method="plane", plane_impl="device")
+    mp = plane["model_param"]
+    rows = mp[2:]
+    is_plane = np.abs(rows[:, :3]).sum(1) > 0
+    assert is_plane.sum() >= 10
+    assert np.all(np.abs(np.linalg.norm(rows[is_plane, :3].astype(np.float64), axis=1) - 1.0) < 1e-5)
+    assert np.array_equal(rows[~is_plane].view(np.uint32), point["model_param"][2:][~is_plane].view(np.uint32))
+    assert len(oracle.write_rpcc(plane["sections"], "bzip2")) < len(oracle.write_rpcc(point["sections"], "bzip2"))
+    rec, _, seg = oracle.decompress_sections(plane["sections"], "Velodyne64E", 0.02)
+    assert np.array_equal(seg, plane["seg_idx"])
+    valid = ri > 0
+    assert float(np.abs(rec - ri)[valid].max()) <= 0.02 + 1e-5
