@@ -15,6 +15,8 @@
 // One CTA per frame; the <= 5000 candidates live in shared memory, one warp scores one hypothesis.
 // The image is read once (pass 1: candidate bit masks + running counts); the kept candidates are then
 // located in the masks by rank, so their loads are independent of one another and all in flight together.
+// oracle/rpcc_oracle.c:orc_ground_fit restates this kernel (samples, summation orders, RPCC_GF_THREADS = 512) and
+// tests/test_gpu_stages.py compares the fitted planes bit for bit: a change of the arithmetic here must be mirrored there.
 #include "ransac.cuh"
 
 namespace rpcc {

@@ -17,6 +17,9 @@
 // the same planes; the fallback mean is the exactly rounded one of point_model_kernel (the
 // reference's plane branch uses numpy's float32 pairwise mean here, <= 1 ulp away).
 //
+// oracle/rpcc_oracle.c:orc_plane_models restates plane_model_kernel (samples, summation orders, 128 threads per CTA) and
+// tests/test_gpu_plane.py compares the model rows byte for byte: a change of the arithmetic here must be mirrored there.
+//
 // Two kernels: label_order_kernel lists every non-empty pixel in the label-major stable order of the
 // symbol stream (so a cluster's pixels are one contiguous slice, found through the same tile offsets
 // quantize.cu uses); plane_model_kernel runs one CTA per (frame, cluster).
