@@ -238,6 +238,20 @@ def test_encoder_with_device_ground_is_byte_exact_against_the_oracle(R, lidar):
                 assert got[k] == v, (lidar, b, k)
 
 
+@pytest.mark.parametrize("method", ["point", "plane"])
+def test_example_frame_with_fitted_ground_matches_the_golden_hash(R, example_points, method):
+    """BASELINE configs[0] with nothing injected: example.bin through the batched encoder (device ground fit, host
+    bzip2) must give the committed .rpcc bytes of tests/golden/example_fitted.json (written by the oracle)."""
+    import json
+    from rpcc_b200.batch import BatchEncoder
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "example_fitted.json")))
+    off = np.array([0, example_points.shape[0]], np.int64)
+    with BatchEncoder("Velodyne64E", accuracy=0.02, max_batch=1, max_points=example_points.shape[0], model_method=method) as enc:
+        blob = enc.compress(example_points, off, None)[0]
+    assert len(blob) == gold[method]["rpcc_bytes"]
+    assert hashlib.sha256(blob).hexdigest() == gold[method]["sha256"]
+
+
 def test_encoder_device_path_and_ground_fit(R):
     """Device-resident inputs, ground fitted on the device: deterministic, close to the true plane, and the
     rest of the chain is byte-exact against the oracle GIVEN that fitted plane."""

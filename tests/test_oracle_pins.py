@@ -204,3 +204,18 @@ def test_oracle_ransac_restatements_behave():
     assert np.array_equal(seg, plane["seg_idx"])
     valid = ri > 0
     assert float(np.abs(rec - ri)[valid].max()) <= 0.02 + 1e-5
+
+
+def test_example_frame_with_fitted_ground_golden(example_points):
+    """The reference's example frame with nothing injected: the oracle (ground RANSAC restatement included) must keep
+    producing the committed bytes; tests/test_gpu_pipeline.py holds the device to the same hashes."""
+    import hashlib
+    import json
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "example_fitted.json")))
+    H, W, hf, vmax, vmin = oracle.lidar_params("Velodyne64E")
+    lut = oracle.transform_map(H, W, hf, vmax, vmin)
+    g = oracle.ground_fit(oracle.project(example_points, H, W, hf, vmax, vmin), lut)
+    assert g.tobytes().hex() == gold["ground_f32_hex"]
+    for name, kw in (("point", {}), ("plane", dict(model_method="plane", plane_impl="device"))):
+        blob = oracle.write_rpcc(oracle.compress_frame(example_points, "Velodyne64E", g, **kw)["sections"], "bzip2")
+        assert len(blob) == gold[name]["rpcc_bytes"] and hashlib.sha256(blob).hexdigest() == gold[name]["sha256"], name
