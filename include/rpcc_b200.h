@@ -72,11 +72,12 @@ RPCC_API int rpcc_project_batch(const float* points, int stride, const int64_t* 
 RPCC_API int rpcc_range_to_xyz_batch(const float* range, const float* lut, int B, int HW, float* xyz, void* stream);
 
 /* a4 (first half). Deterministic ground-plane RANSAC standing in for open3d segment_plane
- * (utils/segment_utils.py:74-82,101-108; parity unpinned, see ground.cu).  Frame b of the batch is
- * keyed by (seed + b), so a frame's plane does not depend on how frames are batched if the caller
- * passes seed = base + index of the first frame.  ground: [B][4] f32, unit normal. */
+ * (utils/segment_utils.py:74-82,101-108; parity unpinned, see ground.cu).  Frame b is keyed by
+ * (seed + frame_keys[b]); frame_keys (device, [B]) may be NULL = key 0 for every frame, in which case a
+ * frame's plane depends on the frame's content alone -- not on its place in the batch, the datalist or
+ * the shard.  ground: [B][4] f32, unit normal. */
 RPCC_API int rpcc_ground_fit_batch(const float* range, const float* lut, int B, int H, int W, uint64_t seed,
-                          float* ground, void* stream);
+                          const uint64_t* frame_keys, float* ground, void* stream);
 
 /* a5. ops/fps/src/sampling_gpu.cu:24-184 furthest_point_sampling_kernel_launcher.
  * points [B][n][3] f32 -> idx [B][m] i32.  Same seeds as the reference kernel, including its
@@ -128,13 +129,14 @@ RPCC_API int rpcc_point_model_batch(const float* range, const uint8_t* labels, c
  * at least min_pixels pixels (reference: 30) and whose plane -- least-squares planes of ransac_n (4)
  * distinct points, `iterations` (10) hypotheses, inliers within dist_thr (0.1 m), refit on the inliers
  * of the best -- passes plane_angle_validation (:84-93) at angle_threshold_deg (cfgs/compressor.yaml:30).
- * Deterministic: keyed by (seed, first_frame + b, label).  open3d's segment_plane is not reproduced
+ * Deterministic: keyed by (seed, frame_keys[b], label); frame_keys as in rpcc_ground_fit_batch (device, NULL = 0).
+ * open3d's segment_plane is not reproduced
  * bit for bit (third-party, randomised; DESIGN.md "parity unpinned"). */
 RPCC_API int rpcc_label_order_batch(const uint8_t* labels, void* book, int B, int H, int W, int K, uint32_t* order,
                            size_t order_stride, void* stream);
 RPCC_API int rpcc_plane_model_batch(const float* range, const float* lut, const uint32_t* order, size_t order_stride,
                            void* book, int B, int H, int W, int K, int min_pixels, float dist_thr, int ransac_n,
-                           int iterations, float angle_threshold_deg, uint64_t seed, uint64_t first_frame,
+                           int iterations, float angle_threshold_deg, uint64_t seed, const uint64_t* frame_keys,
                            float* model, void* stream);
 
 /* a7+a8+a10. cpp_modules.cpp:248-285 intra_predict, :288-334 uniform_quantize (or :337-424 with
@@ -181,6 +183,22 @@ RPCC_API int rpcc_decode_batch(const uint8_t* contour_bits, const uint16_t* seq,
                       int B, int H, int W, int K, uint8_t* labels, float* range_rec, float* xyz, void* book,
                       rpcc_frame_result* results, void* stream);
 
+/* The same for streams packed back to back (what rpcc_encoder_encode_host returns and what a reader of many files
+ * builds): frame b's sequence is seq[seq_base[b] .. seq_base[b+1]) and its symbols symbols[sym_base[b] .. sym_base[b+1])
+ * (u64 [B+1], device). */
+RPCC_API int rpcc_decode_packed_batch(const uint8_t* contour_bits, const uint16_t* seq, const uint64_t* seq_base,
+                             const int16_t* symbols, const uint64_t* sym_base, const float* model, const double* steps,
+                             const float* lut, int B, int H, int W, int K, uint8_t* labels, float* range_rec, float* xyz,
+                             void* book, rpcc_frame_result* results, void* stream);
+
+/* Last step of decoding (dataset/transformer.py:94-101 + save_point_cloud_to_file, dataset/dataset.py:72-81):
+ * range_rec [B][HW] -> rows of (x, y, z, 0) f32 for the pixels with float32 x + y + z != 0, raster order, frames packed
+ * back to back: frame b = rows[4 * row_base[b] .. 4 * row_base[b+1]) (row_base [B+1] u64, device, written here).
+ * rows needs room for B*HW rows; workspace: rpcc_points_workspace_bytes(B, H, W). */
+RPCC_API size_t rpcc_points_workspace_bytes(int B, int H, int W);
+RPCC_API int rpcc_points_out_batch(const float* range_rec, const float* lut, int B, int H, int W, float* rows,
+                          uint64_t* row_base, void* workspace, void* stream);
+
 /* Second half of decoding when the labels are already known; also the batched
  * QuantizationModule.dequantize_residual (utils/compress_utils.py:114-132).  With a zero model and
  * xyz = NULL, range_rec is the dequantised residual itself.  stats_ready = 0 unless `book` already
@@ -200,6 +218,27 @@ RPCC_API int rpcc_chamfer_batch(const float* xyz1, int n, const float* xyz2, int
  * {sum sqrt(dist1), #(dist1 < threshold_sq), sum sqrt(dist2), #(dist2 < threshold_sq)}. */
 RPCC_API int rpcc_chamfer_stats(const float* dist1, int n, const float* dist2, int m, float threshold_sq, double* stats,
                        void* stream);
+
+/* ---- a12 for range images: the --eval figures (tools/compress_datalist.py:166-199, utils/evaluate_metrics.py:9-45) --- */
+/* B pairs (range_ref, range_rec) of range images over the same ray table `lut` ([H][W][3]).  Per frame, metrics
+ * [B][RPCC_EVAL_COLS] f64 =
+ *   0 max |rec - ref|      1 sum |rec - ref| (mean = / HW)
+ *   2 n1 (points of ref with x+y+z != 0)   3 sum sqrt(dist1)   4 #(dist1 < threshold_sq)   5 sum dist1
+ *   6 n2 (points of rec)                    7 sum sqrt(dist2)   8 #(dist2 < threshold_sq)   9 sum dist2
+ *   10 points that needed a whole-image scan   11 label mismatches (labels_ref vs labels_rec; 0 when either is NULL)
+ * dist1 / dist2 = the squared nearest-neighbour distances NmDistanceKernel (chamfer3D.cu:12-154) would return for the
+ * two compacted clouds, found by an exact window search in range-image space (evalq.cu); optional outputs
+ * [B][HW] f32 (-1 at pixels that are not points).  Sums are accumulated in a fixed order (reproducible).
+ * Needs a 360-degree sensor.  workspace: rpcc_eval_workspace_bytes(B, H, W) bytes of device memory. */
+#define RPCC_EVAL_COLS 12
+RPCC_API size_t rpcc_eval_workspace_bytes(int B, int H, int W);
+RPCC_API int rpcc_eval_batch(const float* range_ref, const float* range_rec, const float* lut, const uint8_t* labels_ref,
+                    const uint8_t* labels_rec, int B, int H, int W, double hfov, double vmax, double vmin,
+                    float threshold_sq, float* dist1, float* dist2, double* metrics, void* workspace, void* stream);
+/* steps [B][K] f64 for rpcc_decode_batch: `step` everywhere (salience NULL) or step + level_dacc8[salience[b][l]]
+ * (QuantizationModule, utils/compress_utils.py:48; level_dacc8_dev: 8 doubles on the device). */
+RPCC_API int rpcc_eval_steps_batch(const uint8_t* salience, int B, int K, double step, const double* level_dacc8_dev,
+                          double* steps, void* stream);
 
 /* ================================ host (numpy-facing) ops ==================================== */
 /* One frame, host pointers, synchronous; argument meaning follows the reference's pybind
@@ -274,6 +313,9 @@ typedef struct rpcc_encoder_config {
   float plane_angle_threshold; /* degrees, cfgs/compressor.yaml:30 */
   int host_chunk;              /* encode_host: frames per upload/kernels/download pipeline stage;
                                   0 = one frame per SM of the device, always capped at max_batch */
+  int eval;                    /* 1: every call also decodes what it wrote and fills the --eval figures
+                                  (rpcc_eval_batch; tools/compress_datalist.py:166-199) */
+  float eval_threshold_sq;     /* F-score threshold on the squared distance (0.02^2, utils/evaluate_metrics.py:9) */
 } rpcc_encoder_config;
 
 RPCC_API int rpcc_encoder_create(const rpcc_encoder_config* cfg, rpcc_encoder** out);
@@ -282,38 +324,66 @@ RPCC_API void rpcc_encoder_destroy(rpcc_encoder* enc);
  * frames; results of a call stay in its slot until the slot is used again. */
 RPCC_API int rpcc_encoder_slots(void);
 /* Device-resident inputs (bench `value`): points/offsets as rpcc_project_batch (device pointers),
- * B <= max_batch; ground_in NULL => fitted on device, else [B][4] f32 (device or pinned host).  The
- * deterministic RANSACs (ground plane, cluster planes) are keyed by the frame's index within the call, so
- * the same call always produces the same bytes, however encode_host cuts it into chunks.
+ * B <= max_batch; ground_in NULL => fitted on device, else [B][4] f32 (device or pinned host).
+ * frame_keys: NULL, or [B] u64 on the device -- the keys of the deterministic RANSACs (ground plane, cluster
+ * planes).  With NULL every frame has key 0: its sections depend on its points alone, whatever the batch size,
+ * the frame's position in a datalist, the chunking of encode_host or the number of GPUs the list is sharded over.
  * Enqueues the whole chain on the slot's stream; no synchronisation. */
 RPCC_API int rpcc_encoder_encode_device(rpcc_encoder* enc, int slot, const float* points, int stride,
-                               const int64_t* offsets, int B, const float* ground_in);
+                               const int64_t* offsets, int B, const float* ground_in, const uint64_t* frame_keys);
 /* Host inputs/outputs (bench `e2e`, and what tools/compress_datalist.py calls): any B; frames are
  * cut into chunks of host_chunk (<= max_batch) and pipelined over the slots (upload / kernels / download
  * overlap; the upload of ~1.9 MB per 64E frame over PCIe is what bounds this call, so the chunks are
  * kept small enough that the link never idles behind a kernel batch).
- *   in : points_host rows of `stride` floats, offsets_host [B+1], ground_host [B][4] or NULL (fit on device)
+ *   in : points_host rows of `stride` floats, offsets_host [B+1], ground_host [B][4] or NULL (fit on device),
+ *        frame_keys [B] u64 (host) or NULL as rpcc_encoder_encode_device
  *   out: results [B]; model [B][K][4] f32; contour_bits [B][ceil(HW/8)]; seq: every frame's
  *        idx_sequence back to back (sum seq_count u16, capacity seq_cap entries); symbols likewise
- *        (sum sym_count i16, capacity sym_cap); salience [B][K] u8 (non-uniform; may be NULL).
+ *        (sum sym_count i16, capacity sym_cap); salience [B][K] u8 (non-uniform; may be NULL);
+ *        eval_metrics [B][RPCC_EVAL_COLS] f64 as rpcc_eval_batch fills them (encoder created with eval = 1), or NULL.
  * Pinned host buffers make the copies asynchronous.  Synchronous: returns when everything is on the host. */
 RPCC_API int rpcc_encoder_encode_host(rpcc_encoder* enc, const float* points_host, int stride, const int64_t* offsets_host,
                              int B, const float* ground_host, rpcc_frame_result* results, float* model,
                              uint8_t* contour_bits, uint16_t* seq, size_t seq_cap, int16_t* symbols,
-                             size_t sym_cap, uint8_t* salience);
+                             size_t sym_cap, uint8_t* salience, const uint64_t* frame_keys, double* eval_metrics);
 RPCC_API int rpcc_encoder_sync(rpcc_encoder* enc);
 /* Per-stage device timing with CUDA events recorded on the slots' own streams between the stages of
  * every chain call (at most 256 calls per slot are kept).  rpcc_encoder_profile(enc, 1) starts a fresh
  * recording, (enc, 0) stops it.  rpcc_encoder_stage_times synchronises and returns the summed
- * milliseconds of the 7 stages {project, ground, fps, assign, keypoints, model (+ plane models), quantize}, the frames
+ * milliseconds of the 8 stages {project, ground, fps, assign, keypoints, model (+ plane models), quantize, eval}, the frames
  * they cover and the number of chain calls. */
 RPCC_API int rpcc_encoder_profile(rpcc_encoder* enc, int enable);
 RPCC_API int rpcc_encoder_stage_times(rpcc_encoder* enc, double* ms_out, long long* frames_out, int* calls_out);
 RPCC_API void* rpcc_encoder_stream(rpcc_encoder* enc, int slot);
 /* Named device buffers of a slot (tests, chaining): "range","labels","model","symbols","seq","contour",
  * "results","center_idx","centers","ground","key_points","salience","step_per_label","sym_base",
- * "seq_base","lut","points","offsets","order".  NULL if unknown / not allocated. */
+ * "seq_base","lut","points","offsets","order","eval_range","eval_labels","eval_metrics".  NULL if unknown / not allocated. */
 RPCC_API void* rpcc_encoder_device_buffer(rpcc_encoder* enc, int slot, const char* name);
+
+/* ================================ host entropy stage / file I/O ========================== */
+/* The host side of tools/compress_datalist.py:91-141 as native threads: BasicCompressor.compress_dict +
+ * save_compressed_bitstream (utils/compress_utils.py:167-179,255-310) for every frame of an encode_host call, on a
+ * persistent pool, straight out of the caller's pinned output buffers.  Only method "bzip2" (the reference default,
+ * cfgs/compressor.yaml:2; the system libbz2 at level 9 -- the bytes CPython's bz2.compress writes); deflate / lz4 stay
+ * on the Python pool. */
+typedef struct rpcc_packer rpcc_packer;
+RPCC_API int rpcc_packer_create(int threads, const char* method, rpcc_packer** out);
+RPCC_API void rpcc_packer_destroy(rpcc_packer* pk);
+/* Queue the B frames of one rpcc_encoder_encode_host result (same arrays, same layout: seq / symbols back to back in
+ * frame order).  The arrays must stay untouched until rpcc_packer_wait(*ticket_out) has returned.
+ * paths [B] (entries may be NULL): file to write; bytes_out [B]: file size; status_out [B]; blobs: optional in-memory
+ * copies, frame b at blobs + b * blob_stride (RPCC_ERR_CAPACITY if a file is longer than blob_stride). */
+RPCC_API int rpcc_packer_submit(rpcc_packer* pk, int B, int K, int cbytes, int uniform, const rpcc_frame_result* results,
+                       const float* model, const uint8_t* contour_bits, const uint16_t* seq, const int16_t* symbols,
+                       const uint8_t* salience, const char* const* paths, uint32_t* bytes_out, int* status_out,
+                       uint8_t* blobs, size_t blob_stride, long long* ticket_out);
+RPCC_API int rpcc_packer_wait(rpcc_packer* pk, long long ticket);
+/* dataset/dataset.py:57-63 for a KITTI .bin (rows of x,y,z,intensity f32): the xyz columns into dst (room for
+ * cap_rows rows of 3 floats, typically a slice of the pinned upload buffer); *rows_out = rows in the file. */
+RPCC_API int rpcc_read_bin_xyz(const char* path, float* dst, int64_t cap_rows, int64_t* rows_out);
+/* read_compressed_bitstream + BasicCompressor.decompress_dict (utils/compress_utils.py:182-196,263-310), bzip2:
+ * sections decompressed back to back into dst; sec_len [5] in file order (4 sections when uniform). */
+RPCC_API int rpcc_unpack_rpcc(const uint8_t* blob, size_t n, int uniform, uint8_t* dst, size_t cap, uint32_t* sec_len);
 
 #ifdef __cplusplus
 }

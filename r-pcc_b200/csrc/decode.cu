@@ -64,8 +64,8 @@ constexpr int kDWarps = 8;   // one 1024-pixel tile per warp, 8 tiles of one fra
 // decoded map is kept for validation (point_model_kernel compares it with the sequence length).
 __global__ void __launch_bounds__(kDWarps * 32, 6)
 decode_labels_kernel(const uint8_t* __restrict__ contour_bits, int cbytes, const uint16_t* __restrict__ seq,
-                     size_t seq_stride, const uint32_t* __restrict__ seq_count, int HW, int W, int K, int T,
-                     uint8_t* __restrict__ labels, Book bk) {
+                     size_t seq_stride, const uint32_t* __restrict__ seq_count, const unsigned long long* __restrict__ seq_base,
+                     int HW, int W, int K, int T, uint8_t* __restrict__ labels, Book bk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned* s_cnt = reinterpret_cast<unsigned*>(smem_raw);      // [kDWarps][K]
   const int f = blockIdx.y, tid = threadIdx.x;
@@ -88,8 +88,9 @@ decode_labels_kernel(const uint8_t* __restrict__ contour_bits, int cbytes, const
     }
   }
   unsigned running = bk.tile_coff[(size_t)f * T + tile];
-  const unsigned L = seq_count ? seq_count[f] : 0xFFFFFFFFu;
-  const uint16_t* sq = seq + (size_t)f * seq_stride;
+  // strided streams with optional counts, or streams packed back to back (seq_base [B+1])
+  const unsigned L = seq_base ? (unsigned)(seq_base[f + 1] - seq_base[f]) : (seq_count ? seq_count[f] : 0xFFFFFFFFu);
+  const uint16_t* sq = seq_base ? seq + seq_base[f] : seq + (size_t)f * seq_stride;
   uint8_t* lb = labels + (size_t)f * HW;
   const unsigned lt = lanemask_lt();
   int next_row = ((p_tile + W - 1) / W) * W;       // next pixel that starts an image row
@@ -149,9 +150,9 @@ decode_labels_kernel(const uint8_t* __restrict__ contour_bits, int cbytes, const
 // at counter + (same-label lanes below it).  Then residual = f32((double)q * step), range = pred + residual, xyz = range * LUT.
 __global__ void __launch_bounds__(kDWarps * 32, 6)
 dequant_reconstruct_kernel(const uint8_t* __restrict__ labels, const int16_t* __restrict__ symbols, size_t sym_stride,
-                           const uint32_t* __restrict__ sym_count, const float* __restrict__ model,
-                           const double* __restrict__ steps, const float* __restrict__ lut, Book bk, int HW, int K, int T,
-                           float* __restrict__ range_rec, float* __restrict__ xyz) {
+                           const uint32_t* __restrict__ sym_count, const unsigned long long* __restrict__ sym_base,
+                           const float* __restrict__ model, const double* __restrict__ steps, const float* __restrict__ lut,
+                           Book bk, int HW, int K, int T, float* __restrict__ range_rec, float* __restrict__ xyz) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* s_model = reinterpret_cast<float4*>(smem_raw);        // [K]
   double* s_step = reinterpret_cast<double*>(s_model + K);      // [K]
@@ -171,8 +172,8 @@ dequant_reconstruct_kernel(const uint8_t* __restrict__ labels, const int16_t* __
 
   const int p_tile = tile * kDTile;
   const uint8_t* lb = labels + (size_t)f * HW;
-  const int16_t* sym = symbols + (size_t)f * sym_stride;
-  const unsigned n = sym_count ? sym_count[f] : 0xFFFFFFFFu;
+  const int16_t* sym = sym_base ? symbols + sym_base[f] : symbols + (size_t)f * sym_stride;
+  const unsigned n = sym_base ? (unsigned)(sym_base[f + 1] - sym_base[f]) : (sym_count ? sym_count[f] : 0xFFFFFFFFu);
   float* rr = range_rec + (size_t)f * HW;
   const unsigned lt = lanemask_lt();
 #pragma unroll 2
@@ -217,10 +218,10 @@ using namespace rpcc;
 
 // labels known -> residual / range / xyz.  The second half of decoding, also the batched form of
 // QuantizationModule.dequantize_residual (utils/compress_utils.py:114-132).
-extern "C" int rpcc_dequantize_batch(const uint8_t* labels, const int16_t* symbols, size_t sym_stride,
-                                     const uint32_t* sym_count, const float* model, const double* steps, const float* lut,
-                                     int B, int H, int W, int K, float* range_rec, float* xyz, void* book,
-                                     rpcc_frame_result* results, int stats_ready, void* stream) {
+static int dequantize_impl(const uint8_t* labels, const int16_t* symbols, size_t sym_stride, const uint32_t* sym_count,
+                           const uint64_t* sym_base, const float* model, const double* steps, const float* lut,
+                           int B, int H, int W, int K, float* range_rec, float* xyz, void* book,
+                           rpcc_frame_result* results, int stats_ready, void* stream) {
   RPCC_REQUIRE(labels && symbols && model && steps && lut && range_rec && book && results, "null pointer");
   RPCC_REQUIRE(K >= 2 && K <= 254, "K must be in [2, 254]");
   RPCC_REQUIRE(B <= 65535, "at most 65535 frames per launch");
@@ -238,17 +239,26 @@ extern "C" int rpcc_dequantize_batch(const uint8_t* labels, const int16_t* symbo
   rc = rpcc_point_model_batch(nullptr, labels, nullptr, book, B, H, W, K, nullptr, results, stream);
   if (rc != RPCC_OK) return rc;
   const size_t smem2 = (sizeof(float4) + sizeof(double)) * K + sizeof(unsigned) * (size_t)kDWarps * K;
-  dequant_reconstruct_kernel<<<dim3((T + kDWarps - 1) / kDWarps, B), kDWarps * 32, smem2, st>>>(labels, symbols, sym_stride, sym_count, model, steps, lut,
-                                                                bk, HW, K, T, range_rec, xyz);
+  dequant_reconstruct_kernel<<<dim3((T + kDWarps - 1) / kDWarps, B), kDWarps * 32, smem2, st>>>(
+      labels, symbols, sym_stride, sym_count, reinterpret_cast<const unsigned long long*>(sym_base), model, steps, lut, bk, HW, K,
+      T, range_rec, xyz);
   RPCC_LAUNCH_CHECK("dequant_reconstruct_kernel");
   return RPCC_OK;
 }
 
-extern "C" int rpcc_decode_batch(const uint8_t* contour_bits, const uint16_t* seq, size_t seq_stride,
-                                 const uint32_t* seq_count, const int16_t* symbols, size_t sym_stride,
-                                 const uint32_t* sym_count, const float* model, const double* steps, const float* lut,
-                                 int B, int H, int W, int K, uint8_t* labels, float* range_rec, float* xyz, void* book,
-                                 rpcc_frame_result* results, void* stream) {
+extern "C" int rpcc_dequantize_batch(const uint8_t* labels, const int16_t* symbols, size_t sym_stride,
+                                     const uint32_t* sym_count, const float* model, const double* steps, const float* lut,
+                                     int B, int H, int W, int K, float* range_rec, float* xyz, void* book,
+                                     rpcc_frame_result* results, int stats_ready, void* stream) {
+  return dequantize_impl(labels, symbols, sym_stride, sym_count, nullptr, model, steps, lut, B, H, W, K, range_rec, xyz, book,
+                         results, stats_ready, stream);
+}
+
+static int decode_impl(const uint8_t* contour_bits, const uint16_t* seq, size_t seq_stride, const uint32_t* seq_count,
+                       const uint64_t* seq_base, const int16_t* symbols, size_t sym_stride, const uint32_t* sym_count,
+                       const uint64_t* sym_base, const float* model, const double* steps, const float* lut,
+                       int B, int H, int W, int K, uint8_t* labels, float* range_rec, float* xyz, void* book,
+                       rpcc_frame_result* results, void* stream) {
   RPCC_REQUIRE(contour_bits && seq && symbols && model && steps && lut && labels && range_rec && book && results, "null pointer");
   RPCC_REQUIRE(K >= 2 && K <= 254, "K must be in [2, 254]");
   RPCC_REQUIRE(B <= 65535, "at most 65535 frames per launch");
@@ -262,9 +272,27 @@ extern "C" int rpcc_decode_batch(const uint8_t* contour_bits, const uint16_t* se
   contour_prefix_kernel<<<B, 256, 0, st>>>(contour_bits, cbytes, HW, T, bk);
   RPCC_LAUNCH_CHECK("contour_prefix_kernel");
   const size_t smem1 = sizeof(unsigned) * (size_t)kDWarps * K;
-  decode_labels_kernel<<<dim3((T + kDWarps - 1) / kDWarps, B), kDWarps * 32, smem1, st>>>(contour_bits, cbytes, seq, seq_stride, seq_count, HW, W, K, T,
-                                                          labels, bk);
+  decode_labels_kernel<<<dim3((T + kDWarps - 1) / kDWarps, B), kDWarps * 32, smem1, st>>>(
+      contour_bits, cbytes, seq, seq_stride, seq_count, reinterpret_cast<const unsigned long long*>(seq_base), HW, W, K, T, labels, bk);
   RPCC_LAUNCH_CHECK("decode_labels_kernel");
-  return rpcc_dequantize_batch(labels, symbols, sym_stride, sym_count, model, steps, lut, B, H, W, K, range_rec, xyz, book,
-                               results, 1, stream);
+  return dequantize_impl(labels, symbols, sym_stride, sym_count, sym_base, model, steps, lut, B, H, W, K, range_rec, xyz, book,
+                         results, 1, stream);
+}
+
+extern "C" int rpcc_decode_batch(const uint8_t* contour_bits, const uint16_t* seq, size_t seq_stride,
+                                 const uint32_t* seq_count, const int16_t* symbols, size_t sym_stride,
+                                 const uint32_t* sym_count, const float* model, const double* steps, const float* lut,
+                                 int B, int H, int W, int K, uint8_t* labels, float* range_rec, float* xyz, void* book,
+                                 rpcc_frame_result* results, void* stream) {
+  return decode_impl(contour_bits, seq, seq_stride, seq_count, nullptr, symbols, sym_stride, sym_count, nullptr, model, steps,
+                     lut, B, H, W, K, labels, range_rec, xyz, book, results, stream);
+}
+
+extern "C" int rpcc_decode_packed_batch(const uint8_t* contour_bits, const uint16_t* seq, const uint64_t* seq_base,
+                                        const int16_t* symbols, const uint64_t* sym_base, const float* model,
+                                        const double* steps, const float* lut, int B, int H, int W, int K, uint8_t* labels,
+                                        float* range_rec, float* xyz, void* book, rpcc_frame_result* results, void* stream) {
+  RPCC_REQUIRE(seq_base && sym_base, "null pointer");
+  return decode_impl(contour_bits, seq, 0, nullptr, seq_base, symbols, 0, nullptr, sym_base, model, steps, lut, B, H, W, K,
+                     labels, range_rec, xyz, book, results, stream);
 }

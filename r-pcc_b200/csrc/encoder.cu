@@ -26,6 +26,7 @@ struct Slot {
   float* range = nullptr;       // [B][HW]
   int32_t* scratch = nullptr;   // [B][4]
   float* ground = nullptr;      // [B][4]
+  uint64_t* keys = nullptr;     // [B] caller-supplied RANSAC keys of the chunk (host path staging)
   int32_t* center_idx = nullptr;
   float* centers = nullptr;
   uint8_t* labels = nullptr;
@@ -43,6 +44,14 @@ struct Slot {
   uint32_t* kp_cnt = nullptr;
   void* assign_ws = nullptr;    // centres sorted by norm
   uint32_t* order = nullptr;    // plane modelling: pixels in label-major order [B][HW]
+  // cfg.eval: decode what was just written and compare (tools/compress_datalist.py:166-199)
+  uint8_t* ev_labels = nullptr; // [B][HW]
+  float* ev_range = nullptr;    // [B][HW]
+  void* ev_book = nullptr;
+  rpcc_frame_result* ev_results = nullptr;
+  double* ev_steps = nullptr;   // [B][K]
+  double* ev_metrics = nullptr; // [B][RPCC_EVAL_COLS]
+  void* ev_ws = nullptr;
   // pinned host mirrors for the small per-chunk tables
   rpcc_frame_result* h_results = nullptr;
   int64_t* h_offsets = nullptr;
@@ -54,7 +63,7 @@ struct Slot {
 };
 
 constexpr int kSlots = 3;
-constexpr int kStages = 7;     // project, ground, fps, assign, keypoints, model, quantize
+constexpr int kStages = 8;     // project, ground, fps, assign, keypoints, model, quantize, eval
 constexpr int kEvRing = 256;   // chain calls per slot whose stage events are kept
 
 }  // namespace
@@ -66,6 +75,7 @@ struct rpcc_encoder {
   float hfov, vmax, vmin;
   float level_acc[8];
   float* lut = nullptr;
+  double* dacc8 = nullptr;      // level_dacc on the device (cfg.eval, non-uniform)
   Slot slot[kSlots];
   uint64_t ground_seed = 0x5EEDull;
   bool profiling = false;
@@ -92,6 +102,7 @@ int alloc_slot(rpcc_encoder* e, Slot& s) {
   A(range, B * HW);
   A(scratch, B * 4);
   A(ground, B * 4);
+  A(keys, B);
   A(center_idx, B * m);
   A(centers, B * m * 3);
   A(labels, B * HW);
@@ -109,6 +120,17 @@ int alloc_slot(rpcc_encoder* e, Slot& s) {
     A(kp_cnt, B * K);
   }
   if (e->cfg.model_method == 1) { A(order, B * HW); }
+  if (e->cfg.eval) {
+    A(ev_labels, B * HW);
+    A(ev_range, B * HW);
+    A(ev_results, B);
+    A(ev_steps, B * K);
+    A(ev_metrics, B * RPCC_EVAL_COLS);
+    void* p = nullptr;
+    RPCC_CUDA(cudaMalloc(&p, book_bytes((int)B, e->T, (int)K)));
+    s.ev_book = p;
+    RPCC_CUDA(cudaMalloc(&s.ev_ws, rpcc_eval_workspace_bytes((int)B, e->cfg.H, e->cfg.W)));
+  }
 #undef A
   void* bk = nullptr;
   RPCC_CUDA(cudaMalloc(&bk, book_bytes((int)B, e->T, (int)K)));
@@ -120,9 +142,10 @@ int alloc_slot(rpcc_encoder* e, Slot& s) {
 }
 
 void free_slot(Slot& s) {
-  void* ptrs[] = {s.points, s.offsets, s.range, s.scratch, s.ground, s.center_idx, s.centers, s.labels, s.book, s.model,
+  void* ptrs[] = {s.points, s.offsets, s.range, s.scratch, s.ground, s.keys, s.center_idx, s.centers, s.labels, s.book, s.model,
                   s.results, s.sym_base, s.seq_base, s.symbols, s.seq, s.contour, s.key_points, s.salience,
-                  s.step_per_label, s.kp_cnt, s.assign_ws, s.order};
+                  s.step_per_label, s.kp_cnt, s.assign_ws, s.order, s.ev_labels, s.ev_range, s.ev_book,
+                  s.ev_results, s.ev_steps, s.ev_metrics, s.ev_ws};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s.ev) {
     for (int i = 0; i < kEvRing * (kStages + 1); ++i) if (s.ev[i]) cudaEventDestroy(s.ev[i]);
@@ -136,9 +159,10 @@ void free_slot(Slot& s) {
   s = Slot();
 }
 
-// the kernel chain for B frames whose points are already on the device
+// the kernel chain for B frames whose points are already on the device; frame_keys: device [B] or NULL (key 0: the
+// deterministic RANSACs then depend on the frame's content alone)
 int run_chain(rpcc_encoder* e, Slot& s, const float* points, int stride, const int64_t* offsets, int B,
-              const float* ground_in, uint64_t first_frame) {
+              const float* ground_in, const uint64_t* frame_keys) {
   const rpcc_encoder_config& c = e->cfg;
   void* st = s.stream;
   int rc;
@@ -157,7 +181,7 @@ int run_chain(rpcc_encoder* e, Slot& s, const float* points, int stride, const i
     if (ground_in != s.ground)
       RPCC_CUDA(cudaMemcpyAsync(s.ground, ground_in, sizeof(float) * 4 * (size_t)B, cudaMemcpyDefault, s.stream));
   } else {
-    if ((rc = rpcc_ground_fit_batch(s.range, e->lut, B, c.H, c.W, e->ground_seed + first_frame, s.ground, st))) return rc;
+    if ((rc = rpcc_ground_fit_batch(s.range, e->lut, B, c.H, c.W, e->ground_seed, frame_keys, s.ground, st))) return rc;
   }
   MARK(2);
   if ((rc = rpcc_segment_fps_batch(s.range, e->lut, s.ground, B, c.H, c.W, c.cluster_num, c.ground_threshold,
@@ -176,7 +200,7 @@ int run_chain(rpcc_encoder* e, Slot& s, const float* points, int stride, const i
   if (c.model_method == 1) {
     if ((rc = rpcc_label_order_batch(s.labels, s.book, B, c.H, c.W, e->K, s.order, (size_t)e->HW, st))) return rc;
     if ((rc = rpcc_plane_model_batch(s.range, e->lut, s.order, (size_t)e->HW, s.book, B, c.H, c.W, e->K, 30, 0.1f, 4, 10,
-                                     c.plane_angle_threshold, e->ground_seed ^ 0x9E3779B97F4A7C15ull, first_frame, s.model, st))) return rc;
+                                     c.plane_angle_threshold, e->ground_seed ^ 0x9E3779B97F4A7C15ull, frame_keys, s.model, st))) return rc;
   }
   if ((rc = rpcc_frame_offsets_batch(s.results, B, s.sym_base, s.seq_base, st))) return rc;
   MARK(6);
@@ -184,6 +208,15 @@ int run_chain(rpcc_encoder* e, Slot& s, const float* points, int stride, const i
                                      (float)c.step, B, c.H, c.W, e->K, s.symbols, 0, s.contour, s.seq, 0, s.sym_base,
                                      s.seq_base, st))) return rc;
   MARK(7);
+  if (c.eval) {
+    // decode the sections exactly as they go to the file, then compare with the frame that was encoded
+    if ((rc = rpcc_eval_steps_batch(c.nonuniform ? s.salience : nullptr, B, e->K, c.step, e->dacc8, s.ev_steps, st))) return rc;
+    if ((rc = rpcc_decode_packed_batch(s.contour, s.seq, s.seq_base, s.symbols, s.sym_base, s.model, s.ev_steps, e->lut, B,
+                                       c.H, c.W, e->K, s.ev_labels, s.ev_range, nullptr, s.ev_book, s.ev_results, st))) return rc;
+    if ((rc = rpcc_eval_batch(s.range, s.ev_range, e->lut, s.labels, s.ev_labels, B, c.H, c.W, c.hfov, c.vmax, c.vmin,
+                              c.eval_threshold_sq, nullptr, nullptr, s.ev_metrics, s.ev_ws, st))) return rc;
+  }
+  MARK(8);
 #undef MARK
   s.last_B = B;
   return RPCC_OK;
@@ -230,6 +263,10 @@ extern "C" int rpcc_encoder_create(const rpcc_encoder_config* cfg, rpcc_encoder*
   rc = rpcc_transform_map(cfg->H, cfg->W, cfg->hfov, cfg->vmax, cfg->vmin, lut.data());
   if (rc == RPCC_OK) rc = dev_alloc(&e->lut, lut.size());
   if (rc == RPCC_OK) rc = check_cuda(cudaMemcpy(e->lut, lut.data(), lut.size() * sizeof(float), cudaMemcpyHostToDevice), "lut upload");
+  if (rc == RPCC_OK && cfg->eval) {
+    rc = dev_alloc(&e->dacc8, 8);
+    if (rc == RPCC_OK) rc = check_cuda(cudaMemcpy(e->dacc8, cfg->level_dacc, 8 * sizeof(double), cudaMemcpyHostToDevice), "dacc upload");
+  }
   for (int i = 0; i < kSlots && rc == RPCC_OK; ++i) rc = alloc_slot(e, e->slot[i]);
   if (rc != RPCC_OK) { rpcc_encoder_destroy(e); return rc; }
   *out = e;
@@ -241,6 +278,7 @@ extern "C" void rpcc_encoder_destroy(rpcc_encoder* e) {
   cudaSetDevice(e->cfg.device);
   for (int i = 0; i < kSlots; ++i) free_slot(e->slot[i]);
   if (e->lut) cudaFree(e->lut);
+  if (e->dacc8) cudaFree(e->dacc8);
   delete e;
 }
 
@@ -294,13 +332,13 @@ extern "C" int rpcc_encoder_stage_times(rpcc_encoder* e, double* ms_out, long lo
 }
 
 extern "C" int rpcc_encoder_encode_device(rpcc_encoder* e, int slot, const float* points, int stride,
-                                          const int64_t* offsets, int B, const float* ground_in) {
+                                          const int64_t* offsets, int B, const float* ground_in,
+                                          const uint64_t* frame_keys) {
   RPCC_REQUIRE(e && points && offsets, "null pointer");
   RPCC_REQUIRE(slot >= 0 && slot < kSlots, "bad slot");
   if (B > e->cfg.max_batch) { set_error("rpcc_encoder_encode_device: B=%d exceeds max_batch=%d", B, e->cfg.max_batch); return RPCC_ERR_CAPACITY; }
   RPCC_CUDA(cudaSetDevice(e->cfg.device));
-  // the deterministic RANSACs are keyed by the frame's index within the call: the same call gives the same bytes
-  return run_chain(e, e->slot[slot], points, stride, offsets, B, ground_in, 0);
+  return run_chain(e, e->slot[slot], points, stride, offsets, B, ground_in, frame_keys);
 }
 
 extern "C" int rpcc_encoder_sync(rpcc_encoder* e) {
@@ -321,7 +359,8 @@ extern "C" void* rpcc_encoder_device_buffer(rpcc_encoder* e, int slot, const cha
       {"range", s.range}, {"labels", s.labels}, {"model", s.model}, {"symbols", s.symbols}, {"seq", s.seq},
       {"contour", s.contour}, {"results", s.results}, {"center_idx", s.center_idx}, {"centers", s.centers},
       {"ground", s.ground}, {"key_points", s.key_points}, {"salience", s.salience}, {"step_per_label", s.step_per_label},
-      {"sym_base", s.sym_base}, {"seq_base", s.seq_base}, {"lut", e->lut}, {"points", s.points}, {"offsets", s.offsets}, {"order", s.order}};
+      {"sym_base", s.sym_base}, {"seq_base", s.seq_base}, {"lut", e->lut}, {"points", s.points}, {"offsets", s.offsets}, {"order", s.order},
+      {"eval_range", s.ev_range}, {"eval_labels", s.ev_labels}, {"eval_metrics", s.ev_metrics}};
   for (auto& t : tab) if (strcmp(t.n, name) == 0) return t.p;
   return nullptr;
 }
@@ -333,7 +372,8 @@ extern "C" int rpcc_encoder_encode_host(rpcc_encoder* e, const float* points_hos
                                         const int64_t* offsets_host, int B, const float* ground_host,
                                         rpcc_frame_result* results, float* model, uint8_t* contour_bits,
                                         uint16_t* seq, size_t seq_cap, int16_t* symbols, size_t sym_cap,
-                                        uint8_t* salience) {
+                                        uint8_t* salience, const uint64_t* frame_keys, double* eval_metrics) {
+  RPCC_REQUIRE(!eval_metrics || e == nullptr || e->cfg.eval, "eval_metrics needs an encoder created with eval = 1");
   RPCC_REQUIRE(e && points_host && offsets_host && results && model && contour_bits && seq && symbols, "null pointer");
   RPCC_REQUIRE(stride == 3 || stride == 4, "stride must be 3 or 4");
   RPCC_REQUIRE(B >= 0, "bad batch");
@@ -359,11 +399,16 @@ extern "C" int rpcc_encoder_encode_host(rpcc_encoder* e, const float* points_hos
     RPCC_CUDA(cudaMemcpyAsync(contour_bits + (size_t)p.f0 * cb, s.contour, (size_t)cb * p.nb, cudaMemcpyDeviceToHost, s.stream));
     if (salience && e->cfg.nonuniform)
       RPCC_CUDA(cudaMemcpyAsync(salience + (size_t)p.f0 * K, s.salience, (size_t)K * p.nb, cudaMemcpyDeviceToHost, s.stream));
+    if (eval_metrics)
+      RPCC_CUDA(cudaMemcpyAsync(eval_metrics + (size_t)p.f0 * RPCC_EVAL_COLS, s.ev_metrics, sizeof(double) * RPCC_EVAL_COLS * (size_t)p.nb, cudaMemcpyDeviceToHost, s.stream));
     RPCC_CUDA(cudaEventRecord(s.done, s.stream));
     sym_done += ns; seq_done += nq;
     return RPCC_OK;
   };
 
+  // every exit of the loop -- CUDA error, capacity error -- falls through to the stream synchronisation below: no
+  // copy into the caller's buffers is left in flight when this call returns
+  auto run = [&]() -> int {
   int rc = RPCC_OK;
   for (int c = 0; c < nchunks && rc == RPCC_OK; ++c) {
     // Slot c % kSlots was last used by chunk c - kSlots, which has been finished below (at most two
@@ -385,7 +430,12 @@ extern "C" int rpcc_encoder_encode_host(rpcc_encoder* e, const float* points_hos
       RPCC_CUDA(cudaMemcpyAsync(s.ground, ground_host + (size_t)f0 * 4, sizeof(float) * 4 * nb, cudaMemcpyHostToDevice, s.stream));
       gin = s.ground;
     }
-    rc = run_chain(e, s, s.points, stride, s.offsets, nb, gin, (uint64_t)f0);   // keys: index within this call, not the chunking
+    const uint64_t* kin = nullptr;
+    if (frame_keys) {
+      RPCC_CUDA(cudaMemcpyAsync(s.keys, frame_keys + f0, sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, s.stream));
+      kin = s.keys;
+    }
+    rc = run_chain(e, s, s.points, stride, s.offsets, nb, gin, kin);
     if (rc) break;
     RPCC_CUDA(cudaMemcpyAsync(s.h_results, s.results, sizeof(rpcc_frame_result) * nb, cudaMemcpyDeviceToHost, s.stream));
     RPCC_CUDA(cudaEventRecord(s.done, s.stream));
@@ -395,6 +445,9 @@ extern "C" int rpcc_encoder_encode_host(rpcc_encoder* e, const float* points_hos
     while (pend.size() > 1 && rc == RPCC_OK) { rc = finish(pend.front()); pend.erase(pend.begin()); }
   }
   while (!pend.empty() && rc == RPCC_OK) { rc = finish(pend.front()); pend.erase(pend.begin()); }
+  return rc;
+  };
+  int rc = run();
   for (int i = 0; i < kSlots; ++i) {
     const int r2 = check_cuda(cudaStreamSynchronize(e->slot[i].stream), "stream sync");
     if (rc == RPCC_OK) rc = r2;

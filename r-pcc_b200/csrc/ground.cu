@@ -9,8 +9,10 @@
 // every pixel), the hypothesis shape (10-point least-squares planes, 100 of them), the score
 // (inlier count at 0.1 m, ties by lower rmse) and the final least-squares refit on the inliers of
 // the best hypothesis.  What changes: sampling is counter-based and keyed by
-// (seed, frame), the subsample is an even stride over the candidates in raster order, so the same
-// frame always yields the same plane, on any GPU count.
+// (seed, frame key), the subsample is an even stride over the candidates in raster order.  The frame key
+// is 0 unless the caller supplies one per frame (frame_keys), so by default a frame's plane -- and with
+// it the frame's .rpcc bytes -- depends on the frame's content alone: not on its position in a batch, a
+// datalist or a shard, nor on the GPU count (tests/test_gpu_datalist.py).
 //
 // One CTA per frame; the <= 5000 candidates live in shared memory, one warp scores one hypothesis.
 // The image is read once (pass 1: candidate bit masks + running counts); the kept candidates are then
@@ -42,7 +44,8 @@ __device__ __forceinline__ float plane_dist(float a, float b, float c, float d, 
 
 __global__ void __launch_bounds__(kGfThreads, RPCC_GF_OCC)
 ground_fit_kernel(const float* __restrict__ range, const float* __restrict__ lut, int HW, unsigned long long seed,
-                  float z_below, float inlier_thr, float* __restrict__ ground) {
+                  const unsigned long long* __restrict__ frame_keys, float z_below, float inlier_thr,
+                  float* __restrict__ ground) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* px = reinterpret_cast<float*>(smem_raw);
   float* py = px + kGfPad;
@@ -61,6 +64,7 @@ ground_fit_kernel(const float* __restrict__ range, const float* __restrict__ lut
 
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* rg = range + (size_t)f * HW;
+  const unsigned long long fkey = frame_keys ? frame_keys[f] : 0ull;
 
   // Each warp owns a contiguous segment of the image, so the candidate order is the raster order.
   const int p_begin = warp * seg_len;
@@ -155,7 +159,7 @@ ground_fit_kernel(const float* __restrict__ range, const float* __restrict__ lut
     // reduces it modulo ns (the 64-bit remainder is the expensive part), lane 0 then adds the ten points in order
     int myk = 0;
     if (lane < kGfSample) {
-      unsigned long long st = splitmix64(splitmix64(seed + (unsigned long long)f) ^ ((unsigned long long)it << 40));
+      unsigned long long st = splitmix64(splitmix64(seed + fkey) ^ ((unsigned long long)it << 40));
       for (int j = 0; j <= lane; ++j) st = splitmix64(st);
       myk = (int)(st % (unsigned long long)ns);
     }
@@ -264,14 +268,15 @@ ground_fit_kernel(const float* __restrict__ range, const float* __restrict__ lut
 using namespace rpcc;
 
 extern "C" int rpcc_ground_fit_batch(const float* range, const float* lut, int B, int H, int W, uint64_t seed,
-                                     float* ground, void* stream) {
+                                     const uint64_t* frame_keys, float* ground, void* stream) {
   RPCC_REQUIRE(range && lut && ground, "null pointer");
   if (B == 0) return RPCC_OK;
   const size_t seg_words = (((size_t)H * W + kGfThreads / 32 - 1) / (kGfThreads / 32) + 31) / 32;
   RPCC_REQUIRE((size_t)H * W <= 65535u * (size_t)(kGfThreads / 32), "range image too large for the ground fit");
   const size_t smem = sizeof(float) * 3 * kGfPad + (sizeof(unsigned) + sizeof(unsigned short)) * (size_t)(kGfThreads / 32) * seg_words + 16;
   RPCC_CUDA(cudaFuncSetAttribute(ground_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ground_fit_kernel<<<B, kGfThreads, smem, as_stream(stream)>>>(range, lut, H * W, (unsigned long long)seed, -1.5f, 0.1f, ground);
+  ground_fit_kernel<<<B, kGfThreads, smem, as_stream(stream)>>>(
+      range, lut, H * W, (unsigned long long)seed, reinterpret_cast<const unsigned long long*>(frame_keys), -1.5f, 0.1f, ground);
   RPCC_LAUNCH_CHECK("ground_fit_kernel");
   return RPCC_OK;
 }

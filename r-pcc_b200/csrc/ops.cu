@@ -379,7 +379,7 @@ extern "C" int rpcc_op_ground_fit(const float* range, const float* lut, int H, i
   TRY(upload(d_r, range, HW * sizeof(float)));
   TRY(upload(d_l, lut, HW * 3 * sizeof(float)));
   TRY(d_g.alloc(4 * sizeof(float)));
-  TRY(rpcc_ground_fit_batch(d_r.as<float>(), d_l.as<float>(), 1, H, W, seed, d_g.as<float>(), nullptr));
+  TRY(rpcc_ground_fit_batch(d_r.as<float>(), d_l.as<float>(), 1, H, W, seed, nullptr, d_g.as<float>(), nullptr));
   return download(ground_out, d_g.p, 4 * sizeof(float));
 }
 
@@ -427,7 +427,7 @@ extern "C" int rpcc_op_plane_modeling(const float* range, const int32_t* seg, co
   TRY(d_order.alloc(HW * sizeof(uint32_t)));
   TRY(rpcc_label_order_batch(fb.labels.as<uint8_t>(), fb.book.p, 1, H, W, fb.K, d_order.as<uint32_t>(), HW, nullptr));
   TRY(rpcc_plane_model_batch(fb.range.as<float>(), d_lut.as<float>(), d_order.as<uint32_t>(), HW, fb.book.p, 1, H, W, fb.K,
-                             30, 0.1f, 4, 10, angle_threshold_deg, seed, 0, fb.model.as<float>(), nullptr));
+                             30, 0.1f, 4, 10, angle_threshold_deg, seed, nullptr, fb.model.as<float>(), nullptr));
   *rows = fb.K - 1;
   return download(rows_out, fb.model.as<float>() + 4, sizeof(float) * 4 * (size_t)(fb.K - 1));
 }

@@ -13,8 +13,9 @@
 // by the lower rmse; the winner is refitted on its inliers; the angle test reproduces the reference's
 // expression including its precedence quirk (|n.s| / |n| * |s|) and numpy's NaN
 // semantics (arccos of a value above 1 is NaN, a NaN maximum compares false => the plane is kept).
-// What changes: sampling is counter-based and keyed by (seed, frame, label), so a frame always gets
-// the same planes; the fallback mean is the exactly rounded one of point_model_kernel (the
+// What changes: sampling is counter-based and keyed by (seed, frame key, label) -- the frame key is 0
+// unless the caller supplies one per frame, so a frame always gets the same planes wherever it sits in a
+// batch or a datalist; the fallback mean is the exactly rounded one of point_model_kernel (the
 // reference's plane branch uses numpy's float32 pairwise mean here, <= 1 ulp away).
 //
 // oracle/rpcc_oracle.c:orc_plane_models restates plane_model_kernel (samples, summation orders, 128 threads per CTA) and
@@ -79,7 +80,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 __global__ void __launch_bounds__(kPlThreads, 7)
 plane_model_kernel(const float* __restrict__ range, const float* __restrict__ lut, const unsigned* __restrict__ order,
                    size_t order_stride, Book bk, int HW, int K, int T, int min_pixels, float dist_thr, int ransac_n, int iters,
-                   double cos_thr, unsigned long long seed, unsigned long long first_frame, float* __restrict__ model) {
+                   double cos_thr, unsigned long long seed, const unsigned long long* __restrict__ frame_keys,
+                   float* __restrict__ model) {
   extern __shared__ __align__(16) float4 s_pt[];     // [kPlCap] ray.x, ray.y, ray.z, range
   __shared__ double s_plane[kPlMaxIter][4];
   __shared__ double s_err[kPlMaxIter][kPlWarps];
@@ -113,7 +115,7 @@ plane_model_kernel(const float* __restrict__ range, const float* __restrict__ lu
 
   // ---- hypotheses: thread `it` draws ransac_n distinct points and fits their least-squares plane
   if (tid < iters) {
-    unsigned long long st = splitmix64(splitmix64(seed + first_frame + (unsigned long long)f) ^
+    unsigned long long st = splitmix64(splitmix64(seed + (frame_keys ? frame_keys[f] : 0ull)) ^
                                        ((unsigned long long)l << 48) ^ ((unsigned long long)tid << 32));
     unsigned pick[kPlMaxSample];
     double s[10];
@@ -247,7 +249,7 @@ extern "C" int rpcc_label_order_batch(const uint8_t* labels, void* book, int B, 
 
 extern "C" int rpcc_plane_model_batch(const float* range, const float* lut, const uint32_t* order, size_t order_stride,
                                       void* book, int B, int H, int W, int K, int min_pixels, float dist_thr, int ransac_n,
-                                      int iterations, float angle_threshold_deg, uint64_t seed, uint64_t first_frame,
+                                      int iterations, float angle_threshold_deg, uint64_t seed, const uint64_t* frame_keys,
                                       float* model, void* stream) {
   RPCC_REQUIRE(range && lut && order && book && model, "null pointer");
   RPCC_REQUIRE(K >= 2 && K <= 254, "K must be in [2, 254]");
@@ -261,7 +263,7 @@ extern "C" int rpcc_plane_model_batch(const float* range, const float* lut, cons
   const double cos_thr = cos(3.14159265358979323846 * ((double)angle_threshold_deg / 180.0));
   plane_model_kernel<<<dim3(K - 2, B), kPlThreads, sizeof(float4) * kPlCap, as_stream(stream)>>>(
       range, lut, order, order_stride, bk, HW, K, T, min_pixels, dist_thr, ransac_n, iterations, cos_thr,
-      (unsigned long long)seed, (unsigned long long)first_frame, model);
+      (unsigned long long)seed, reinterpret_cast<const unsigned long long*>(frame_keys), model);
   RPCC_LAUNCH_CHECK("plane_model_kernel");
   return RPCC_OK;
 }

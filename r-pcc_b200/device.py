@@ -111,3 +111,23 @@ def quantize_pack_batch(rng, labels, model, lut, book, step, step_per_label=None
                                               ptr(step_per_label), C.c_float(step), B, H, W, K, ptr(symbols),
                                               C.c_size_t(HW), ptr(contour), ptr(seq), C.c_size_t(HW), None, None, _stream()))
     return symbols, contour, seq
+
+
+def eval_batch(range_ref, range_rec, lut, lidar, labels_ref=None, labels_rec=None, f1_threshold=0.02, want_dist=False):
+    """The --eval figures for B pairs of range images over one ray table (rpcc_eval_batch, csrc/evalq.cu).
+    -> (metrics (B, 12) f64 cuda, dist1 (B,H,W) f32 | None, dist2 | None); dist* are the squared nearest-neighbour
+    distances of the reference's chamfer kernel, -1 at pixels that are not points."""
+    _need_cuda(range_ref, range_rec, lut, labels_ref, labels_rec)
+    B = range_ref.shape[0]
+    H, W = lidar.H, lidar.W
+    from .batch import EVAL_COLS
+    metrics = torch.empty((B, EVAL_COLS), dtype=torch.float64, device=range_ref.device)
+    _lib.lib().rpcc_eval_workspace_bytes.restype = C.c_size_t
+    ws = torch.empty((_lib.lib().rpcc_eval_workspace_bytes(B, H, W),), dtype=torch.uint8, device=range_ref.device)
+    d1 = torch.empty((B, H, W), dtype=torch.float32, device=range_ref.device) if want_dist else None
+    d2 = torch.empty((B, H, W), dtype=torch.float32, device=range_ref.device) if want_dist else None
+    check(_lib.lib().rpcc_eval_batch(ptr(range_ref), ptr(range_rec), ptr(lut), ptr(labels_ref), ptr(labels_rec), B, H, W,
+                                     C.c_double(lidar.horizontal_FOV), C.c_double(lidar.vertical_max),
+                                     C.c_double(lidar.vertical_min), C.c_float(f1_threshold ** 2), ptr(d1), ptr(d2),
+                                     ptr(metrics), ptr(ws), _stream()))
+    return metrics, d1, d2

@@ -79,17 +79,20 @@ def compress(args, ground_model=None):
         point_cloud_rec = dataset.PCTransformer.range_image_to_point_cloud(range_image_rec)
         range_dif = np.abs(range_image_rec - range_image)
         max_depth_error, mean_depth_error = np.max(range_dif), np.mean(range_dif)
-        # the reference constructs these errors without raising them (tools/compress.py:176-181)
-        bound = accuracy + 0.00001 if uniform else accuracy + 0.06 + 0.00001
-        if max_depth_error > bound:
-            raise AssertionError("Reconstruction error... Please check...")
         chamfer = calc_chamfer_distance(point_cloud, point_cloud_rec, out=False)
         print("\nReconstruction quality: ")
         print("    Depth Error (mean): ", mean_depth_error)
         print("    Depth Error (max): ", max_depth_error)
         print("    Chamfer Distance (mean): ", chamfer["mean"])
         print("    F1 score (threshold=0.02): ", chamfer["f_score"])
-        result.update(max_depth_error=float(max_depth_error), chamfer_mean=chamfer["mean"], f_score=chamfer["f_score"])
+        # the reference constructs an AssertionError here without raising it (tools/compress.py:176-181) and goes on to
+        # print the table; same behaviour, with the message made visible
+        bound = accuracy + 0.00001 if uniform else accuracy + 0.06 + 0.00001
+        if max_depth_error > bound:
+            print("    WARNING: Reconstruction error... Please check... (max depth error %g > %g: a residual wrapped "
+                  "int16 or a model row is not finite)" % (max_depth_error, bound))
+        result.update(max_depth_error=float(max_depth_error), mean_depth_error=float(mean_depth_error),
+                      chamfer_mean=chamfer["mean"], f_score=chamfer["f_score"], within_bound=bool(max_depth_error <= bound))
     return result
 
 

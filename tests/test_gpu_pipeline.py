@@ -231,7 +231,7 @@ def test_encoder_with_device_ground_is_byte_exact_against_the_oracle(R, lidar):
         out = enc.encode_host(pts, off, None)
         for b in range(len(seeds)):
             p = pts[off[b]:off[b + 1]]
-            g = oracle.ground_fit(oracle.project(p, H, W, hf, vmax, vmin), lut, seed=0x5EED, frame=b)
+            g = oracle.ground_fit(oracle.project(p, H, W, hf, vmax, vmin), lut, seed=0x5EED)
             want = oracle.compress_frame(p, lidar, g)["sections"]
             got = BatchEncoder.frame_sections(out, b)
             for k, v in want.items():

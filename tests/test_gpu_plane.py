@@ -124,9 +124,9 @@ def test_plane_models_match_their_restatement_byte_for_byte(frames, accuracy):
             out = enc.encode_host(pts, off, grounds if inject else None)
             for b in range(B):
                 p = pts[off[b]:off[b + 1]]
-                g = grounds[b] if inject else oracle.ground_fit(oracle.project(p, H, W, hf, vmax, vmin), lut, frame=b)
+                g = grounds[b] if inject else oracle.ground_fit(oracle.project(p, H, W, hf, vmax, vmin), lut)
                 want = oracle.compress_frame(p, "Velodyne64E", g, accuracy=accuracy, model_method="plane",
-                                             plane_impl="device", frame=b)
+                                             plane_impl="device")
                 got = BatchEncoder.frame_sections(out, b)
                 assert got["plane_param"] == want["sections"]["plane_param"], (accuracy, inject, b)
                 for k, v in want["sections"].items():

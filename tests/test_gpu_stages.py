@@ -293,18 +293,23 @@ def test_ground_fit_matches_its_restatement(T, R, lidar):
             got = seg.ransac_plane_segmentation(ris[b], seed=seed)
             want = oracle.ground_fit(ris[b], lut, seed=seed, frame=0)
             assert got.tobytes() == want.tobytes(), (lidar, b, seed, got, want)
-    # batched kernel: frame b of the launch is keyed seed + b
+    # batched kernel: without frame keys every frame is keyed 0 (its plane depends on its content alone); with
+    # caller-supplied keys frame b is keyed seed + keys[b]
     import ctypes as C
     from rpcc_b200 import _lib
     from rpcc_b200._lib import check, ptr
     d_lut = T.from_numpy(lut).cuda()
     d_g = T.empty((len(seeds), 4), dtype=T.float32, device="cuda")
-    check(_lib.lib().rpcc_ground_fit_batch(ptr(rng), ptr(d_lut), len(seeds), cfg.H, cfg.W, C.c_uint64(0x5EED), ptr(d_g),
-                                           C.c_void_p(T.cuda.current_stream().cuda_stream)))
-    T.cuda.synchronize()
-    got = d_g.cpu().numpy()
-    for b in range(len(seeds)):
-        assert got[b].tobytes() == oracle.ground_fit(ris[b], lut, seed=0x5EED, frame=b).tobytes(), (lidar, b)
+    keys = np.array([0, 11, 5, 1 << 40, 3], np.uint64)
+    d_keys = T.from_numpy(keys.view(np.int64)).cuda()
+    for dk, hk in ((None, np.zeros(len(seeds), np.uint64)), (d_keys, keys)):
+        check(_lib.lib().rpcc_ground_fit_batch(ptr(rng), ptr(d_lut), len(seeds), cfg.H, cfg.W, C.c_uint64(0x5EED),
+                                               ptr(dk) if dk is not None else None, ptr(d_g),
+                                               C.c_void_p(T.cuda.current_stream().cuda_stream)))
+        T.cuda.synchronize()
+        got = d_g.cpu().numpy()
+        for b in range(len(seeds)):
+            assert got[b].tobytes() == oracle.ground_fit(ris[b], lut, seed=0x5EED, frame=int(hk[b])).tobytes(), (lidar, b)
     # no ground below the sensor: fewer than 800 candidates -> all pixels (utils/segment_utils.py:105-106)
     bare = np.where(ris[0] * lut[..., 2] < -1.5, 0.0, ris[0]).astype(np.float32)
     assert seg.ransac_plane_segmentation(bare).tobytes() == oracle.ground_fit(bare, lut).tobytes()

@@ -157,3 +157,52 @@ def test_default_workers_split_the_cores_over_the_local_ranks(monkeypatch):
     assert batch.default_workers() == 1
     monkeypatch.setenv("LOCAL_WORLD_SIZE", "junk")
     assert batch.default_workers() == 31
+
+
+def test_native_packer_writes_the_bytes_python_bz2_would(tmp_path):
+    """csrc/hostio.cu (host-only code: runs without a GPU): the native entropy pool must write, for every frame of an
+    encode_host-shaped result, exactly save_compressed_bitstream(compress_dict(...)) of utils/compress_utils.py:167-179,
+    255-310 -- uniform and non-uniform, to files and to memory -- and rpcc_unpack_rpcc / rpcc_read_bin_xyz must invert /
+    match numpy."""
+    from rpcc_b200 import synthetic
+    from rpcc_b200.batch import RESULT_DTYPE
+    from rpcc_b200.hostio import Packer, read_bin_xyz, unpack_rpcc
+    B, K = 3, 102
+    frames = [synthetic.frame(60 + i, "VelodyneVLP16") for i in range(B)]
+    secs = [oracle.compress_frame(p, "VelodyneVLP16", g, nonuniform=True)["sections"] for p, g in frames]
+    cb = len(secs[0]["contour_map"])
+    res = np.zeros(B, RESULT_DTYPE)
+    model, contour, sal = np.zeros((B, K, 4), np.float32), np.zeros((B, cb), np.uint8), np.zeros((B, K), np.uint8)
+    seq, sym = [], []
+    for b, s in enumerate(secs):
+        rows = len(s["plane_param"]) // 16
+        res[b] = (len(s["residual_quantized"]) // 2, len(s["idx_sequence"]) // 2, rows, 0)
+        model[b, :rows] = np.frombuffer(s["plane_param"], np.float32).reshape(-1, 4)
+        contour[b] = np.frombuffer(s["contour_map"], np.uint8)
+        sal[b, :rows] = np.frombuffer(s["salience_level"], np.uint8)
+        seq.append(np.frombuffer(s["idx_sequence"], np.uint16))
+        sym.append(np.frombuffer(s["residual_quantized"], np.int16))
+    enc = dict(results=res, model=model, contour=contour, seq=np.concatenate(seq), symbols=np.concatenate(sym), salience=sal)
+    pk = Packer(3)
+    paths = [str(tmp_path / ("%d.rpcc" % b)) for b in range(B)]
+    sizes, blobs = pk.wait(pk.submit(enc, K, False, paths, keep=True))
+    for b in range(B):
+        want = oracle.write_rpcc(secs[b])
+        assert open(paths[b], "rb").read() == want and blobs[b, :sizes[b]].tobytes() == want
+        back = unpack_rpcc(want, False, 1 << 20)
+        assert all(back[k].tobytes() == secs[b][k] for k in secs[b])
+    enc["salience"] = None
+    sizes, blobs = pk.wait(pk.submit(enc, K, True, None, keep=True))
+    for b in range(B):
+        s = {k: v for k, v in secs[b].items() if k != "salience_level"}
+        assert blobs[b, :sizes[b]].tobytes() == oracle.write_rpcc(s)
+    with pytest.raises(Exception):
+        pk.wait(pk.submit(enc, K, True, [str(tmp_path / "no_such_dir" / "x.rpcc")] * B))
+    pk.close()
+    f = tmp_path / "a.bin"
+    frames[0][0].tofile(str(f))
+    dst = np.zeros((frames[0][0].shape[0] + 5, 3), np.float32)
+    assert read_bin_xyz(str(f), dst) == frames[0][0].shape[0]
+    assert np.array_equal(dst[:frames[0][0].shape[0]], frames[0][0][:, :3])
+    with pytest.raises(Exception):
+        read_bin_xyz(str(f), dst[:10])
