@@ -4,7 +4,11 @@
 published algorithm (least-squares planes of `ransac_n` random points, inlier count at the threshold, ties
 by rmse, refit on the inliers).  All hypotheses are fitted and scored in a handful of array operations (about 2 ms for
 the 100 x 5000 ground problem of utils/segment_utils.py:101-108), so the stand-in is not slower than the multi-threaded
-C++ it replaces by more than that.  The sampler is numpy's global RNG, unseeded like the reference's own subsample."""
+C++ it replaces by more than that.  The sampler is numpy's global RNG, unseeded like the reference's own subsample.
+With RPCC_STUB_GROUND="a,b,c,d" in the environment the 10-point call (the ground fit, utils/segment_utils.py:79-81) returns
+that model instead: the parity tests inject one ground plane into every implementation they compare."""
+import os
+
 import numpy as np
 
 
@@ -37,6 +41,9 @@ class _PointCloud:
     def segment_plane(self, distance_threshold=0.1, ransac_n=3, num_iterations=100):
         pts = np.asarray(self.points, np.float64).reshape(-1, 3)
         n = pts.shape[0]
+        fixed = os.environ.get("RPCC_STUB_GROUND")
+        if fixed and ransac_n == 10:
+            return np.array([float(x) for x in fixed.split(",")]), []
         if n < ransac_n:
             return np.array([0.0, 0.0, 1.0, 0.0]), []
         idx = np.argsort(np.random.random((num_iterations, n)), axis=1)[:, :ransac_n] if n <= 64 else \
