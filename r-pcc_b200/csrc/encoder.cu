@@ -16,6 +16,15 @@
 
 using namespace rpcc;
 
+namespace rpcc {
+// quantize.cu; trusted_labels: the labels come from assign_labels_kernel and are < K by construction
+template <typename SymT>
+int quantize_pack_launch(const float* range, const uint8_t* labels, const float* model, const float* lut, void* book,
+                         const float* step_per_label, float step, int B, int H, int W, int K, SymT* symbols,
+                         size_t sym_stride, uint8_t* contour_bits, uint16_t* seq, size_t seq_stride,
+                         const uint64_t* sym_base, const uint64_t* seq_base, void* stream, bool trusted_labels);
+}
+
 namespace {
 
 struct Slot {
@@ -204,9 +213,9 @@ int run_chain(rpcc_encoder* e, Slot& s, const float* points, int stride, const i
   }
   if ((rc = rpcc_frame_offsets_batch(s.results, B, s.sym_base, s.seq_base, st))) return rc;
   MARK(6);
-  if ((rc = rpcc_quantize_pack_batch(s.range, s.labels, s.model, e->lut, s.book, c.nonuniform ? s.step_per_label : nullptr,
-                                     (float)c.step, B, c.H, c.W, e->K, s.symbols, 0, s.contour, s.seq, 0, s.sym_base,
-                                     s.seq_base, st))) return rc;
+  if ((rc = quantize_pack_launch<int16_t>(s.range, s.labels, s.model, e->lut, s.book, c.nonuniform ? s.step_per_label : nullptr,
+                                          (float)c.step, B, c.H, c.W, e->K, s.symbols, 0, s.contour, s.seq, 0, s.sym_base,
+                                          s.seq_base, st, true))) return rc;
   MARK(7);
   if (c.eval) {
     // decode the sections exactly as they go to the file, then compare with the frame that was encoded

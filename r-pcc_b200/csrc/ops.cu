@@ -16,7 +16,7 @@ template <typename SymT>
 int quantize_pack_launch(const float* range, const uint8_t* labels, const float* model, const float* lut, void* book,
                          const float* step_per_label, float step, int B, int H, int W, int K, SymT* symbols,
                          size_t sym_stride, uint8_t* contour_bits, uint16_t* seq, size_t seq_stride,
-                         const uint64_t* sym_base, const uint64_t* seq_base, void* stream);
+                         const uint64_t* sym_base, const uint64_t* seq_base, void* stream, bool trusted_labels);
 }
 
 namespace {
@@ -116,7 +116,7 @@ int quantize_common(FrameBook& fb, int H, int W, const float* step_per_label_dev
   // utils/compress_utils.py:142)
   TRY(quantize_pack_launch<int32_t>(fb.range.as<float>(), fb.labels.as<uint8_t>(), zero_model.as<float>(), lut.as<float>(),
                                     fb.book.p, step_per_label_dev, step, 1, H, W, fb.K, sym.as<int32_t>(), HW,
-                                    contour.as<uint8_t>(), seq.as<uint16_t>(), HW, nullptr, nullptr, nullptr));
+                                    contour.as<uint8_t>(), seq.as<uint16_t>(), HW, nullptr, nullptr, nullptr, false));
   *n_out = (int64_t)fb.res.sym_count;
   return download(out, sym.p, (size_t)fb.res.sym_count * sizeof(int32_t));
 }

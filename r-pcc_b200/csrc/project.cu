@@ -15,7 +15,7 @@
 // are unfused (-fmad=false), division and sqrt are IEEE.
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "async.cuh"
 
 namespace rpcc {
 
@@ -113,34 +113,7 @@ constexpr int kDeferCap = 2048;     // points per CTA and frame whose pixel is r
 template <int THREADS>
 constexpr size_t proj_smem() { return sizeof(float4) * (ProjStages<THREADS>::value * THREADS * kPPT + kDeferCap) + 16 * ProjStages<THREADS>::value + 64; }
 
-// ---- mbarrier / bulk-copy primitives (sm_90+ PTX; SASS: SYNCS.*, UBLKCP)
-__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned a, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned a) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned a, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned a, unsigned parity) {
-  asm volatile(
-      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
-      ::"r"(a), "r"(parity) : "memory");
-}
-__device__ __forceinline__ float4 lds_f4(unsigned a) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
-  return v;
-}
-// global -> shared bulk copy (16-byte aligned, size a multiple of 16), completion credited to `mbar`;
-// the points are read exactly once: L2 evict-first so that they do not push the range images out
-__device__ __forceinline__ void bulk_load(unsigned dst, const void* src, unsigned bytes, unsigned mbar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-      ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar), "l"(0x12F0000000000000ull) : "memory");
-}
+// mbarrier / bulk-copy primitives: async.cuh (SASS: SYNCS.*, UBLKCP)
 
 // Fast pixel derivation with a proof obligation instead of exactness.  Division-free arctangents
 // (odd minimax polynomials: degree 17 on [0,1] for the azimuth, |error| <= 1.0e-7 rad evaluated in f32;
