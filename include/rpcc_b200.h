@@ -46,7 +46,9 @@ extern "C" {
 #define RPCC_ERR_NO_DEVICE (-3)
 #define RPCC_ERR_CAPACITY (-4) /* caller-provided buffer too small / batch larger than the encoder's */
 
-#define RPCC_MAX_LABELS 256   /* labels are stored as u8 on device; K = cluster_num + 2 <= 254 */
+#define RPCC_MAX_LABELS 256   /* labels are stored as u8 on device; K = cluster_num + 2 <= 254, i.e. --cluster_num <= 252
+                                 (the reference's idx_sequence is uint16 and accepts more; tools/common.py rejects larger
+                                 values with a message) */
 #define RPCC_TILE 1024        /* pixels per rank tile (flat raster index / 1024) */
 
 RPCC_API const char* rpcc_last_error(void);
@@ -104,12 +106,9 @@ RPCC_API size_t rpcc_book_bytes(int B, int H, int W, int K);
 
 /* a4 (second half, utils/segment_utils.py:143-148,168-169) + a6 accumulation
  * (cpp_modules.cpp:471-518): per-pixel argmin over {ground, m centres} with torch's float32
- * arithmetic.  labels [B][HW] u8.  Fills `book` (K = m + 2) for the next two stages.
- * workspace: rpcc_assign_workspace_bytes(B, m) bytes of device memory. */
+ * arithmetic.  labels [B][HW] u8.  Fills `book` (K = m + 2) for the next two stages. */
 RPCC_API int rpcc_assign_labels_batch(const float* range, const float* lut, const float* ground, const float* centers,
-                             int B, int H, int W, int m, uint8_t* labels, void* book, void* workspace, void* stream);
-/* device scratch for the above (centres sorted by norm, per frame) */
-RPCC_API size_t rpcc_assign_workspace_bytes(int B, int m);
+                             int B, int H, int W, int m, uint8_t* labels, void* book, void* stream);
 
 /* Same bookkeeping for callers that bring their own labels (the standalone quantize ops). */
 RPCC_API int rpcc_label_stats_batch(const float* range, const uint8_t* labels, int B, int H, int W, int K,

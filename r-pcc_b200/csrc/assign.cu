@@ -273,12 +273,10 @@ extern "C" size_t rpcc_book_bytes(int B, int H, int W, int K) {
   return book_bytes(B, T, K);
 }
 
-extern "C" size_t rpcc_assign_workspace_bytes(int B, int m) { (void)B; (void)m; return 16; }  // kept for ABI stability: unused
 
 extern "C" int rpcc_assign_labels_batch(const float* range, const float* lut, const float* ground, const float* centers,
-                                        int B, int H, int W, int m, uint8_t* labels, void* book, void* workspace,
+                                        int B, int H, int W, int m, uint8_t* labels, void* book,
                                         void* stream) {
-  (void)workspace;
   RPCC_REQUIRE(range && lut && ground && centers && labels && book, "null pointer");
   RPCC_REQUIRE(m >= 1 && m + 2 <= RPCC_MAX_LABELS, "cluster_num must be in [1, 254]");
   RPCC_REQUIRE(B <= 65535, "at most 65535 frames per launch");

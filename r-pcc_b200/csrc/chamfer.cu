@@ -59,11 +59,17 @@ __global__ void chamfer_unpack_kernel(const unsigned long long* __restrict__ bes
   idx[i] = (int)(unsigned)(k & 0xFFFFFFFFull);
 }
 
-// stats[0] = sum sqrt(d) (f64), stats[1] = #(d < thr) (as f64)
-__global__ void chamfer_stats_kernel(const float* __restrict__ dist, int n, float thr, double* __restrict__ stats) {
+// stats[0] = sum sqrt(d) (f64), stats[1] = #(d < thr) (as f64).  One CTA per direction; every thread walks a fixed
+// stride, partial sums meet in a fixed order (xor tree inside a warp, warps in index order): the figures are
+// reproducible from run to run (an atomicAdd of doubles is not).
+constexpr int kStThreads = 1024;
+__global__ void __launch_bounds__(kStThreads)
+chamfer_stats_kernel(const float* __restrict__ dist, int n, float thr, double* __restrict__ stats) {
+  __shared__ double s_sum[kStThreads / 32];
+  __shared__ unsigned s_cnt[kStThreads / 32];
   double s = 0.0;
   unsigned c = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (int i = threadIdx.x; i < n; i += kStThreads) {
     const float d = dist[i];
     s += (double)sqrtf(d);
     c += d < thr ? 1u : 0u;
@@ -73,9 +79,14 @@ __global__ void chamfer_stats_kernel(const float* __restrict__ dist, int n, floa
     s += __shfl_xor_sync(0xffffffffu, s, o);
     c += __shfl_xor_sync(0xffffffffu, c, o);
   }
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&stats[0], s);
-    atomicAdd(&stats[1], (double)c);
+  if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = s; s_cnt[threadIdx.x >> 5] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    unsigned long long k = 0;
+    for (int w = 0; w < kStThreads / 32; ++w) { t += s_sum[w]; k += s_cnt[w]; }
+    stats[0] = t;
+    stats[1] = (double)k;
   }
 }
 
@@ -120,7 +131,7 @@ extern "C" int rpcc_chamfer_stats(const float* dist1, int n, const float* dist2,
   RPCC_REQUIRE(dist1 && dist2 && stats, "null pointer");
   cudaStream_t st = as_stream(stream);
   RPCC_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(double), st));
-  if (n > 0) { chamfer_stats_kernel<<<min(1024, (n + 255) / 256), 256, 0, st>>>(dist1, n, threshold_sq, stats); RPCC_LAUNCH_CHECK("chamfer_stats_kernel"); }
-  if (m > 0) { chamfer_stats_kernel<<<min(1024, (m + 255) / 256), 256, 0, st>>>(dist2, m, threshold_sq, stats + 2); RPCC_LAUNCH_CHECK("chamfer_stats_kernel"); }
+  if (n > 0) { chamfer_stats_kernel<<<1, kStThreads, 0, st>>>(dist1, n, threshold_sq, stats); RPCC_LAUNCH_CHECK("chamfer_stats_kernel"); }
+  if (m > 0) { chamfer_stats_kernel<<<1, kStThreads, 0, st>>>(dist2, m, threshold_sq, stats + 2); RPCC_LAUNCH_CHECK("chamfer_stats_kernel"); }
   return RPCC_OK;
 }

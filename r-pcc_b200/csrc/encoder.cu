@@ -51,7 +51,6 @@ struct Slot {
   uint8_t* salience = nullptr;
   float* step_per_label = nullptr;
   uint32_t* kp_cnt = nullptr;
-  void* assign_ws = nullptr;    // centres sorted by norm
   uint32_t* order = nullptr;    // plane modelling: pixels in label-major order [B][HW]
   // cfg.eval: decode what was just written and compare (tools/compress_datalist.py:166-199)
   uint8_t* ev_labels = nullptr; // [B][HW]
@@ -144,7 +143,6 @@ int alloc_slot(rpcc_encoder* e, Slot& s) {
   void* bk = nullptr;
   RPCC_CUDA(cudaMalloc(&bk, book_bytes((int)B, e->T, (int)K)));
   s.book = bk;
-  RPCC_CUDA(cudaMalloc(&s.assign_ws, rpcc_assign_workspace_bytes((int)B, (int)m)));
   RPCC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&s.h_results), sizeof(rpcc_frame_result) * B));
   RPCC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&s.h_offsets), sizeof(int64_t) * (B + 1)));
   return RPCC_OK;
@@ -153,7 +151,7 @@ int alloc_slot(rpcc_encoder* e, Slot& s) {
 void free_slot(Slot& s) {
   void* ptrs[] = {s.points, s.offsets, s.range, s.scratch, s.ground, s.keys, s.center_idx, s.centers, s.labels, s.book, s.model,
                   s.results, s.sym_base, s.seq_base, s.symbols, s.seq, s.contour, s.key_points, s.salience,
-                  s.step_per_label, s.kp_cnt, s.assign_ws, s.order, s.ev_labels, s.ev_range, s.ev_book,
+                  s.step_per_label, s.kp_cnt, s.order, s.ev_labels, s.ev_range, s.ev_book,
                   s.ev_results, s.ev_steps, s.ev_metrics, s.ev_ws};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s.ev) {
@@ -196,7 +194,7 @@ int run_chain(rpcc_encoder* e, Slot& s, const float* points, int stride, const i
   if ((rc = rpcc_segment_fps_batch(s.range, e->lut, s.ground, B, c.H, c.W, c.cluster_num, c.ground_threshold,
                                    s.center_idx, s.centers, st))) return rc;
   MARK(3);
-  if ((rc = rpcc_assign_labels_batch(s.range, e->lut, s.ground, s.centers, B, c.H, c.W, c.cluster_num, s.labels, s.book, s.assign_ws, st))) return rc;
+  if ((rc = rpcc_assign_labels_batch(s.range, e->lut, s.ground, s.centers, B, c.H, c.W, c.cluster_num, s.labels, s.book, st))) return rc;
   MARK(4);
   if (c.nonuniform) {
     if ((rc = rpcc_keypoints_salience_batch(s.range, s.labels, s.book, B, c.H, c.W, e->K, c.feature_region, c.segments,

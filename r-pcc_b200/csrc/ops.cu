@@ -325,8 +325,7 @@ extern "C" int rpcc_op_segment(const float* range, const float* lut, const float
                                float ground_thr, int32_t* seg_out, int32_t* center_idx_out) {
   RPCC_REQUIRE(range && lut && ground && seg_out, "null pointer");
   const size_t HW = (size_t)H * W;
-  DevBuf d_rng, d_lut, d_g, d_ci, d_c, d_lab, d_book, d_ws;
-  TRY(d_ws.alloc(rpcc_assign_workspace_bytes(1, m)));
+  DevBuf d_rng, d_lut, d_g, d_ci, d_c, d_lab, d_book;
   TRY(upload(d_rng, range, HW * sizeof(float)));
   TRY(upload(d_lut, lut, HW * 3 * sizeof(float)));
   TRY(upload(d_g, ground, 4 * sizeof(float)));
@@ -337,7 +336,7 @@ extern "C" int rpcc_op_segment(const float* range, const float* lut, const float
   TRY(rpcc_segment_fps_batch(d_rng.as<float>(), d_lut.as<float>(), d_g.as<float>(), 1, H, W, m, ground_thr, d_ci.as<int32_t>(),
                              d_c.as<float>(), nullptr));
   TRY(rpcc_assign_labels_batch(d_rng.as<float>(), d_lut.as<float>(), d_g.as<float>(), d_c.as<float>(), 1, H, W, m,
-                               d_lab.as<uint8_t>(), d_book.p, d_ws.p, nullptr));
+                               d_lab.as<uint8_t>(), d_book.p, nullptr));
   std::vector<uint8_t> lab(HW);
   TRY(download(lab.data(), d_lab.p, HW));
   for (size_t p = 0; p < HW; ++p) seg_out[p] = lab[p];

@@ -9,10 +9,11 @@
 //   .astype(np.int16)                      (utils/compress_utils.py:142, wraps)
 //   contour_utils_cpp.extract_contour + np.packbits + astype(uint16)   (:521-558, compress_utils.py:155-160)
 //
-// HBM-bound: reads 4 B (range) + 1 B (label) per pixel, writes 2 B per valid pixel + 1 bit per pixel
-// + 2 B per run.  One CTA = one 1024-pixel tile (one pixel per thread).  The stable rank of a pixel
-// inside (tile, label) comes from match_any inside its warp plus a per-label scan over the 32 warps
-// in shared memory; the tile's base comes from tile_off (model.cu).
+// Reads 4 B (range) + 1 B (label) per pixel, writes 2 B per valid pixel + 1 bit per pixel + 2 B per run.
+// One WARP = one 1024-pixel tile, 8 tiles of a frame per CTA; the tile's range values and labels arrive in shared
+// memory through two bulk copies (TMA engine) that complete on the warp's own mbarrier.  The stable rank of a pixel
+// inside (tile, label) is a per-warp counter in shared memory, seeded from tile_off (model.cu), plus the pixel's
+// rank among the same-label lanes of its 32-pixel slice (match_any): no block-level synchronisation.
 #include <stdlib.h>
 
 #include "async.cuh"

@@ -73,10 +73,8 @@ def assign_labels_batch(rng, lut, ground, centers, book=None):
     labels = torch.empty((B, H, W), dtype=torch.uint8, device=rng.device)
     if book is None:
         book = new_book(B, H, W, m + 2, rng.device)
-    _lib.lib().rpcc_assign_workspace_bytes.restype = C.c_size_t
-    ws = torch.empty((_lib.lib().rpcc_assign_workspace_bytes(B, m),), dtype=torch.uint8, device=rng.device)
     check(_lib.lib().rpcc_assign_labels_batch(ptr(rng), ptr(lut), ptr(ground), ptr(centers), B, H, W, m,
-                                              ptr(labels), ptr(book), ptr(ws), _stream()))
+                                              ptr(labels), ptr(book), _stream()))
     return labels, book
 
 

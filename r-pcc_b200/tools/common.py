@@ -53,4 +53,8 @@ def resolve(args):
     if args.angle_threshold is not None:
         model_cfg["angle_threshold"] = args.angle_threshold
     uniform = False if args.nonuniform else cfg["compress_framework"] == "uniform"
+    if not 1 <= int(segment_cfg["cluster_num"]) <= 252:
+        # labels are bytes on the device (0 ground, 1 empty, 2.. clusters; RPCC_MAX_LABELS in include/rpcc_b200.h); the
+        # reference's uint16 idx_sequence would allow more
+        raise SystemExit("--cluster_num must be in [1, 252] on this path (got %s)" % segment_cfg["cluster_num"])
     return cfg, accuracy, segment_cfg, model_cfg, uniform, method
