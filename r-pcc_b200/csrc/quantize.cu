@@ -31,6 +31,10 @@ constexpr int kQThreads = kQWarps * 32;
 #endif
 constexpr int kQSlices = RPCC_QSLICES;      // 32-pixel slices per step: that many independent loads in flight per lane
 constexpr int kQSteps = RPCC_TILE / (32 * kQSlices);
+#ifndef RPCC_QUNROLL
+#define RPCC_QUNROLL 1
+#endif
+constexpr int kQUnroll = RPCC_QUNROLL;      // steps per loop iteration
 
 // stores into the two output streams: 64-bit base (kept in one register pair) + 32-bit element index
 __device__ __forceinline__ void stg_elem(int16_t* base, unsigned i, int v) {
@@ -84,7 +88,7 @@ __device__ __forceinline__ void quantize_tile(const float* __restrict__ rg, cons
   unsigned myword = 0;                           // contour word of slice `lane` of the tile
   asm volatile("" : "+l"(sym), "+l"(sq));        // keep the two stream bases in one register pair each
 
-#pragma unroll 1
+#pragma unroll kQUnroll
   for (int s = 0; s < kQSteps; ++s) {
     const int p_step = p_tile + s * (32 * kQSlices);
     if (!FULL && p_step >= HW) break;
