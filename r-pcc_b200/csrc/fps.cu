@@ -24,8 +24,6 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include <cuda_fp16.h>
-
 #include "common.cuh"
 
 namespace rpcc {
@@ -560,328 +558,6 @@ static int launch_fps_pruned(const float* range, const float* lut, const float* 
 }
 
 
-// ------------------------------------------------------------------------------------------------
-// fused mask + FPS, two-level pruning, bucket state in shared memory: one CTA per frame
-// ------------------------------------------------------------------------------------------------
-// segment_fps_pruned_kernel above spends most of its instructions around the updates, not in them: every round it tests
-// all ~4000 bucket boxes (13 %), reduces ~4000 per-bucket maxima held in registers (10 %), and its first pass costs 150
-// instructions per bucket (30 %).  The buckets that really change are ~60-120 per round and sit in a handful of places.
-// Here the buckets (still 32 consecutive pixels) are grouped into SUPER-BUCKETS -- the buckets whose first pixel lies
-// in one 8-row x 128-column block of the range image, at most 32 of them, compact in space -- and a round is
-//   1. super tests   every warp tests the boxes of its own few super-buckets (one lane each) against the new centre;
-//                    only for the ~5-10 that can change are the member buckets tested (one lane each), and the
-//                    buckets that can change are appended to a work list in shared memory;
-//   2. updates       the work list is dealt out round-robin to ALL warps (a compact region would otherwise land on a
-//                    few warps): the reference arithmetic on the bucket's 32 points, new maximum / tie key to shared;
-//   3. winner        the super-buckets that were touched re-derive their maximum from their buckets' state; every
-//                    warp then reduces the <= 128 super maxima.
-// The bucket state (maximum, tie key: 8 bytes) and the bucket boxes (fp16, rounded outwards: 12 bytes) live in
-// shared memory, so ownership of a test and of an update can differ.  Pruning is conservative at both levels
-// (boxes only ever grow by rounding; the test carries a relative slack) and touched points are updated with the
-// reference's own arithmetic, so the seed sequence is the reference's, bit for bit (tests/test_gpu_stages.py).
-constexpr int kHSupRows = 8, kHSupCols = 128;
-constexpr int kHMaxSupers = 128, kHMaxBuckets = 4096, kHQueue = 4096;
-constexpr unsigned kHNone = 0xFFFFu;
-
-struct HierSmem {                      // byte offsets inside the dynamic shared memory block
-  unsigned rec, tk, sa, sb, slot, queue, alist, end;
-};
-__host__ __device__ inline HierSmem hier_layout(int NB) {
-  HierSmem L;
-  const unsigned nbp = (unsigned)((NB + 3) & ~3);
-  L.rec = 0;                                       // uint4 [nbp]: box x, y, z as fp16 (min, max) pairs; maximum t (bits)
-  L.tk = L.rec + nbp * 16u;                        // u32 [nbp]: tie key of the point holding the maximum
-  L.sa = L.tk + nbp * 4u;                          // float4 [128]: super-bucket box x0, x1, y0, y1
-  L.sb = L.sa + kHMaxSupers * 16u;                 // uint4 [128]: z0, z1 (float bits), maximum t, tie key
-  L.slot = L.sb + kHMaxSupers * 16u;               // u16 [128][32]: bucket of slot t of super s, or kHNone
-  L.queue = L.slot + kHMaxSupers * 32u * 2u;       // u16 [kHQueue]
-  L.alist = L.queue + kHQueue * 2u;                // u8 [128]: super-buckets touched this round
-  L.end = L.alist + kHMaxSupers;
-  return L;
-}
-
-__device__ __forceinline__ unsigned pack_box(float lo, float hi) {   // fp16 pair, rounded outwards
-  unsigned short a, b;
-  asm("cvt.rm.f16.f32 %0, %1;" : "=h"(a) : "f"(lo));
-  asm("cvt.rp.f16.f32 %0, %1;" : "=h"(b) : "f"(hi));
-  return (unsigned)a | ((unsigned)b << 16);
-}
-__device__ __forceinline__ float2 unpack_box(unsigned v) {
-  const __half2 h = *reinterpret_cast<const __half2*>(&v);
-  return __half22float2(h);
-}
-// squared distance from the point to the box (0 inside); +inf for an empty box (lo = +inf, hi = -inf)
-__device__ __forceinline__ float box_lb(float x0, float x1, float y0, float y1, float z0, float z1, float cx, float cy, float cz) {
-  const float ox = fmaxf(fmaxf(x0 - cx, cx - x1), 0.f);
-  const float oy = fmaxf(fmaxf(y0 - cy, cy - y1), 0.f);
-  const float oz = fmaxf(fmaxf(z0 - cz, cz - z1), 0.f);
-  return __fmaf_rn(oz, oz, __fmaf_rn(oy, oy, ox * ox));
-}
-__device__ __forceinline__ unsigned tie_of(int p) { return (__brev((unsigned)p) & 0xFFC00000u) | ((unsigned)p >> 10); }
-
-#ifndef RPCC_FPS_ILP
-#define RPCC_FPS_ILP 2
-#endif
-
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 2)
-segment_fps_hier_kernel(const float* __restrict__ range, const float* __restrict__ lut, const float* __restrict__ ground,
-                        int B, int H, int W, int m, float thr, unsigned* __restrict__ temp_ws, int* __restrict__ next_frame,
-                        int* __restrict__ center_idx, float* __restrict__ centers) {
-  constexpr int NW = THREADS / 32;
-  constexpr int ILP = RPCC_FPS_ILP;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int HW = H * W, NB = (HW + 31) >> 5;
-  const int NCG = (W + kHSupCols - 1) / kHSupCols, NS = ((H + kHSupRows - 1) / kHSupRows) * NCG;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const HierSmem L = hier_layout(NB);
-  uint4* s_rec = reinterpret_cast<uint4*>(smem_raw + L.rec);
-  unsigned* s_tk = reinterpret_cast<unsigned*>(smem_raw + L.tk);
-  float4* s_sa = reinterpret_cast<float4*>(smem_raw + L.sa);
-  uint4* s_sb = reinterpret_cast<uint4*>(smem_raw + L.sb);
-  unsigned short* s_slot = reinterpret_cast<unsigned short*>(smem_raw + L.slot);
-  unsigned short* s_queue = reinterpret_cast<unsigned short*>(smem_raw + L.queue);
-  unsigned char* s_alist = smem_raw + L.alist;
-  __shared__ int s_frame;
-  __shared__ int s_qn[2], s_an[2];
-  unsigned* temp = temp_ws + (size_t)blockIdx.x * HW;
-  const float INF = __int_as_float(0x7f800000);
-
-  // ---- slot table: the buckets of every super-bucket (the same for every frame)
-  for (int s = tid; s < NS; s += THREADS) {
-    const int r0 = (s / NCG) * kHSupRows, c0 = (s % NCG) * kHSupCols;
-    for (int rr = 0; rr < kHSupRows; ++rr) {
-      const int r = r0 + rr;
-      int b_lo = 0, b_hi = 0;
-      if (r < H) {
-        b_lo = (r * W + c0 + 31) >> 5;
-        b_hi = (r * W + min(c0 + kHSupCols, W) + 31) >> 5;
-      }
-      for (int i = 0; i < 4; ++i) s_slot[s * 32 + rr * 4 + i] = (unsigned short)(b_lo + i < b_hi ? b_lo + i : (int)kHNone);
-    }
-  }
-  if (tid == 0) { s_qn[0] = s_qn[1] = 0; s_an[0] = s_an[1] = 0; }
-
-  for (;;) {
-    __syncthreads();                       // slot table / previous frame done
-    if (tid == 0) s_frame = atomicAdd(next_frame, 1);
-    __syncthreads();
-    const int f = s_frame;
-    if (f >= B) break;
-    const float* rg = range + (size_t)f * HW;
-    const float g0 = ground[f * 4], g1 = ground[f * 4 + 1], g2 = ground[f * 4 + 2], g3 = ground[f * 4 + 3];
-    const float gnorm = sqrtf(torch_sum3(g0 * g0, g1 * g1, g2 * g2));
-    float x1, y1, z1;                      // seed 0 is flat index 0 (sampling_gpu.cu:44-46)
-    masked_point(rg[0], lut, g0, g1, g2, g3, gnorm, thr, x1, y1, z1);
-    if (tid == 0) {
-      center_idx[(size_t)f * m] = 0;
-      float* c = centers + (size_t)f * m * 3;
-      c[0] = x1; c[1] = y1; c[2] = z1;
-    }
-    // ---- first pass = round 1 over every bucket: t = min(d, 1e10); bucket maxima, tie keys, boxes; super-bucket boxes
-    for (int s = warp; s < NS; s += NW) {
-      unsigned smax = 0u, stk = kNoTie;
-      float sx0 = INF, sy0 = INF, sz0 = INF, sx1 = -INF, sy1 = -INF, sz1 = -INF;
-#pragma unroll 2
-      for (int t = 0; t < 32; ++t) {
-        const unsigned b = s_slot[s * 32 + t];
-        if (b == kHNone) continue;                             // warp-uniform
-        const int p = (int)(b << 5) + lane;
-        const bool inb = p < HW;
-        float x = 0.f, y = 0.f, z = 0.f;
-        if (inb) masked_point(rg[p], lut + (size_t)p * 3, g0, g1, g2, g3, gnorm, thr, x, y, z);
-        const bool origin = (x == 0.f) && (y == 0.f) && (z == 0.f);
-        const float tv = fminf(fps_dist(x, y, z, x1, y1, z1), 1e10f);
-        if (inb) temp[p] = __float_as_uint(tv) | (origin ? 0x80000000u : 0u);
-        const unsigned nb = inb ? __float_as_uint(tv) : 0u;
-        const unsigned newmax = __reduce_max_sync(0xffffffffu, nb);
-        if (newmax == 0u) {                                    // nothing here can ever be chosen or change
-          if (lane == 0) { s_rec[b] = make_uint4(0xFC007C00u, 0xFC007C00u, 0xFC007C00u, 0u); s_tk[b] = kNoTie; }   // box (+inf, -inf)
-          continue;
-        }
-        const unsigned ntk = __reduce_min_sync(0xffffffffu, (inb && nb == newmax) ? tie_of(p) : kNoTie);
-        // box over the points that can still change (t > 0).  Coordinates are shifted into (0, 512) so that their
-        // bit patterns order like the values (one REDUX each); the shift rounds to 3e-5 m, which the 1e-4 m added
-        // on either side and the outward fp16 rounding cover.
-        const bool live = inb && tv > 0.f;
-        float a0, a1, a2, a3, a4, a5;
-        if (!__any_sync(0xffffffffu, live && !(fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) < 250.f))) {
-          const unsigned ux = __float_as_uint(x + 256.f), uy = __float_as_uint(y + 256.f), uz = __float_as_uint(z + 256.f);
-          a0 = __uint_as_float(__reduce_min_sync(0xffffffffu, live ? ux : 0x7f800000u)) - 256.0001f;
-          a1 = __uint_as_float(__reduce_min_sync(0xffffffffu, live ? uy : 0x7f800000u)) - 256.0001f;
-          a2 = __uint_as_float(__reduce_min_sync(0xffffffffu, live ? uz : 0x7f800000u)) - 256.0001f;
-          a3 = __uint_as_float(__reduce_max_sync(0xffffffffu, live ? ux : 0u)) - 255.9999f;
-          a4 = __uint_as_float(__reduce_max_sync(0xffffffffu, live ? uy : 0u)) - 255.9999f;
-          a5 = __uint_as_float(__reduce_max_sync(0xffffffffu, live ? uz : 0u)) - 255.9999f;
-        } else {                                               // coordinates beyond any lidar's range (or NaN): exact order
-          const int big = 0x7fffffff;
-          a0 = ordf(__reduce_min_sync(0xffffffffu, live ? ford(x) : big));
-          a1 = ordf(__reduce_min_sync(0xffffffffu, live ? ford(y) : big));
-          a2 = ordf(__reduce_min_sync(0xffffffffu, live ? ford(z) : big));
-          a3 = ordf(__reduce_max_sync(0xffffffffu, live ? ford(x) : -big));
-          a4 = ordf(__reduce_max_sync(0xffffffffu, live ? ford(y) : -big));
-          a5 = ordf(__reduce_max_sync(0xffffffffu, live ? ford(z) : -big));
-        }
-        if (lane == 0) { s_rec[b] = make_uint4(pack_box(a0, a3), pack_box(a1, a4), pack_box(a2, a5), newmax); s_tk[b] = ntk; }
-        if (newmax > smax || (newmax == smax && ntk < stk)) { smax = newmax; stk = ntk; }
-        sx0 = fminf(sx0, a0); sy0 = fminf(sy0, a1); sz0 = fminf(sz0, a2);
-        sx1 = fmaxf(sx1, a3); sy1 = fmaxf(sy1, a4); sz1 = fmaxf(sz1, a5);
-      }
-      if (lane == 0) {
-        s_sa[s] = make_float4(sx0, sx1, sy0, sy1);
-        s_sb[s] = make_uint4(__float_as_uint(sz0), __float_as_uint(sz1), smax, stk);
-      }
-    }
-    __syncthreads();
-
-    for (int j = 1; j < m; ++j) {
-      const int par = j & 1;
-      // ---- winner of the previous round (in round 1: of the first pass): every warp reduces the super maxima
-      {
-        unsigned d = 0u, tk = kNoTie;
-        for (int s = lane; s < NS; s += 32) {
-          const uint2 v = *reinterpret_cast<const uint2*>(&s_sb[s].z);
-          const bool better = v.x > d || (v.x == d && v.y < tk);
-          d = better ? v.x : d; tk = better ? v.y : tk;
-        }
-        const unsigned dmax = __reduce_max_sync(0xffffffffu, d);
-        const unsigned tkmin = __reduce_min_sync(0xffffffffu, d == dmax ? tk : kNoTie);
-        const int k = (int)(((tkmin & 0x3FFFFFu) << 10) | __brev(tkmin & 0xFFC00000u));
-        // all five loads leave together (volatile asm: the compiler would otherwise predicate the last four on the first)
-        const float r = ld_stream_f(rg + k);
-        const float wx = ld_stream_f(lut + (size_t)k * 3), wy = ld_stream_f(lut + (size_t)k * 3 + 1), wz = ld_stream_f(lut + (size_t)k * 3 + 2);
-        const bool org = (temp[k] >> 31) != 0u;
-        x1 = org ? 0.f : r * wx; y1 = org ? 0.f : r * wy; z1 = org ? 0.f : r * wz;
-        if (tid == 0) {
-          center_idx[(size_t)f * m + j] = k;
-          float* c = centers + ((size_t)f * m + j) * 3;
-          c[0] = x1; c[1] = y1; c[2] = z1;
-          s_qn[par ^ 1] = 0; s_an[par ^ 1] = 0;               // the other parity's lists are idle during this round
-        }
-      }
-      if (j == m - 1) break;                                  // the last centre needs no update pass
-      // ---- 1. which super-buckets, and inside them which buckets, can change?
-      {
-        const int s = warp + NW * lane;                        // lane i tests this warp's i-th super-bucket
-        bool sa = false;
-        if (s < NS) {
-          const float4 a = s_sa[s];
-          const uint4 bq = s_sb[s];
-          const float lb = box_lb(a.x, a.y, a.z, a.w, __uint_as_float(bq.x), __uint_as_float(bq.y), x1, y1, z1);
-          sa = lb * 0.9999f < __uint_as_float(bq.z);
-        }
-        unsigned am = __ballot_sync(0xffffffffu, sa);
-        while (am) {
-          const int i = __ffs(am) - 1;
-          am &= am - 1;
-          const int ss = warp + NW * i;
-          const unsigned b = s_slot[ss * 32 + lane];
-          bool act = false;
-          if (b != kHNone) {
-            const uint4 rc = s_rec[b];
-            const float2 bx = unpack_box(rc.x), by = unpack_box(rc.y), bz = unpack_box(rc.z);
-            act = box_lb(bx.x, bx.y, by.x, by.y, bz.x, bz.y, x1, y1, z1) * 0.9999f < __uint_as_float(rc.w);
-          }
-          const unsigned ab = __ballot_sync(0xffffffffu, act);
-          if (ab) {
-            int base = 0;
-            if (lane == 0) { base = atomicAdd(&s_qn[par], __popc(ab)); s_alist[atomicAdd(&s_an[par], 1)] = (unsigned char)ss; }
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (act) s_queue[base + __popc(ab & lanemask_lt())] = (unsigned short)b;
-          }
-        }
-      }
-      __syncthreads();
-      // ---- 2. update them with the reference arithmetic: the list is dealt out over all warps, ILP buckets per warp
-      //      and iteration with all their loads in flight together (the loads are what a round waits for)
-      {
-        const int qn = s_qn[par];
-        const float* rgl = rg + lane;
-        const float* lutl = lut + 3 * lane;
-        unsigned* tpl = temp + lane;
-        for (int i = warp; i < qn; i += ILP * NW) {
-          unsigned bq[ILP], tb[ILP];
-          float r[ILP], lx[ILP], ly[ILP], lz[ILP];
-          bool on[ILP];
-#pragma unroll
-          for (int u = 0; u < ILP; ++u) {
-            const int iu = i + u * NW;
-            bq[u] = s_queue[iu < qn ? iu : i];
-            on[u] = iu < qn && (int)(bq[u] << 5) + lane < HW;
-            tb[u] = 0u; r[u] = 0.f; lx[u] = 0.f; ly[u] = 0.f; lz[u] = 0.f;
-            if (on[u]) {
-              const unsigned o = bq[u] << 5;
-              tb[u] = tpl[o];
-              r[u] = __ldg(rgl + o);
-              lx[u] = __ldg(lutl + 3 * o); ly[u] = __ldg(lutl + 3 * o + 1); lz[u] = __ldg(lutl + 3 * o + 2);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < ILP; ++u) {
-            if (i + u * NW >= qn) break;                       // warp-uniform
-            unsigned nb = 0u;
-            if (on[u]) {
-              const bool org = (tb[u] >> 31) != 0u;
-              const float x = org ? 0.f : r[u] * lx[u], y = org ? 0.f : r[u] * ly[u], z = org ? 0.f : r[u] * lz[u];
-              const float told = __uint_as_float(tb[u] & 0x7fffffffu);
-              const float tn = fminf(fps_dist(x, y, z, x1, y1, z1), told);          // sampling_gpu.cu:64-66
-              nb = __float_as_uint(tn);
-              if (tn != told) tpl[bq[u] << 5] = nb | (tb[u] & 0x80000000u);
-            }
-            const unsigned newmax = __reduce_max_sync(0xffffffffu, nb);
-            const unsigned ntk = __reduce_min_sync(0xffffffffu, (on[u] && nb == newmax) ? tie_of((int)(bq[u] << 5) + lane) : kNoTie);
-            if (lane == 0) { s_rec[bq[u]].w = newmax; s_tk[bq[u]] = ntk; }
-          }
-        }
-      }
-      __syncthreads();
-      // ---- 3. the touched super-buckets re-derive their maximum
-      {
-        const int an = s_an[par];
-        for (int i = warp; i < an; i += NW) {
-          const int ss = s_alist[i];
-          const unsigned b = s_slot[ss * 32 + lane];
-          unsigned vx = 0u, vy = kNoTie;
-          if (b != kHNone) { vx = s_rec[b].w; vy = s_tk[b]; }
-          const unsigned dmax = __reduce_max_sync(0xffffffffu, vx);
-          const unsigned tkmin = __reduce_min_sync(0xffffffffu, vx == dmax ? vy : kNoTie);
-          if (lane == 0) *reinterpret_cast<uint2*>(&s_sb[ss].z) = make_uint2(dmax, tkmin);
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
-template <int THREADS>
-static int launch_fps_hier(const float* range, const float* lut, const float* ground, int B, int H, int W, int m, float thr,
-                           int* center_idx, float* centers, cudaStream_t st) {
-  auto kern = segment_fps_hier_kernel<THREADS>;
-  const int HW = H * W, NB = (HW + 31) / 32;
-  const size_t smem = hier_layout(NB).end;
-  RPCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  RPCC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
-  if (per_sm < 1) per_sm = 1;
-  int grid = per_sm * sm_count();
-  if (grid > B) grid = B;
-  void* ws = nullptr;
-  cudaMemPool_t pool = nullptr;
-  { const int rc = scratch_pool(&pool); if (rc != RPCC_OK) return rc; }
-  const size_t ws_bytes = sizeof(unsigned) * (size_t)grid * HW;
-  RPCC_CUDA(cudaMallocFromPoolAsync(&ws, ws_bytes + 256, pool, st));
-  int* counter = reinterpret_cast<int*>(static_cast<unsigned char*>(ws) + ws_bytes);   // frame queue head
-  cudaError_t le = cudaMemsetAsync(counter, 0, sizeof(int), st);
-  if (le == cudaSuccess) {
-    kern<<<grid, THREADS, smem, st>>>(range, lut, ground, B, H, W, m, thr, static_cast<unsigned*>(ws), counter, center_idx, centers);
-    le = cudaGetLastError();
-  }
-  RPCC_CUDA(cudaFreeAsync(ws, st));
-  RPCC_CUDA(le);
-  count_launch();
-  return RPCC_OK;
-}
-
 }  // namespace rpcc
 
 using namespace rpcc;
@@ -905,18 +581,6 @@ extern "C" int rpcc_segment_fps_batch(const float* range, const float* lut, cons
   RPCC_REQUIRE(m >= 1, "need at least one seed");
   if (B == 0) return RPCC_OK;
   static const bool use_cluster = getenv("RPCC_FPS_IMPL") && !strcmp(getenv("RPCC_FPS_IMPL"), "cluster");
-  static const bool use_pruned = getenv("RPCC_FPS_IMPL") && !strcmp(getenv("RPCC_FPS_IMPL"), "pruned");
-  {
-    const int NBh = (HW + 31) / 32;
-    const int NSh = ((H + kHSupRows - 1) / kHSupRows) * ((W + kHSupCols - 1) / kHSupCols);
-    if (!use_cluster && !use_pruned && m >= 2 && NBh <= kHMaxBuckets && NSh <= kHMaxSupers && W >= kHSupCols) {
-      static const int ht = getenv("RPCC_FPS_THREADS") ? atoi(getenv("RPCC_FPS_THREADS")) : 1024;
-      cudaStream_t st = as_stream(stream);
-      if (ht == 512) return launch_fps_hier<512>(range, lut, ground, B, H, W, m, ground_thr, center_idx, centers, st);
-      if (ht == 768) return launch_fps_hier<768>(range, lut, ground, B, H, W, m, ground_thr, center_idx, centers, st);
-      return launch_fps_hier<1024>(range, lut, ground, B, H, W, m, ground_thr, center_idx, centers, st);
-    }
-  }
   static const int fps_threads = getenv("RPCC_FPS_THREADS") ? atoi(getenv("RPCC_FPS_THREADS")) : 1024;
   if (!use_cluster && m >= 2) {
     cudaStream_t st = as_stream(stream);
