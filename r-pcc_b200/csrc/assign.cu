@@ -177,25 +177,21 @@ assign_labels_kernel(const float* __restrict__ range, const float* __restrict__ 
       label = 0;                                       // every residual of the slice is below the skip threshold
     }
     if (inb) lb[p] = (uint8_t)label;
-    // ---- per-label count and exact range sum (range * 2^28 as u64, see the header), private bins
+    // ---- per-label count and exact range sum (range * 2^28 as u64, see the header), private bins: the lanes of a
+    //      label form a group (match_any), the group's sums come from two reductions over that group, its lowest
+    //      lane adds them to the warp's bins -- one pass, however many labels the slice holds
     {
-      unsigned todo = __ballot_sync(0xffffffffu, inb);
       const bool exact = !(inb && label >= 2) || (r >= 0.03125f && r < 256.0f);
       if (!__all_sync(0xffffffffu, exact)) flag |= 1u;
       const unsigned long long v = inb ? (unsigned long long)((double)r * 268435456.0) : 0ull;
-      while (todo) {
-        const int leader = __ffs(todo) - 1;
-        const int l = __shfl_sync(0xffffffffu, label, leader);
-        const bool mine = inb && label == l;
-        const unsigned grp = __ballot_sync(0xffffffffu, mine);
-        if (l >= 2) {
-          // v < 2^36: split so that 32 addends cannot overflow 32 bits
-          const unsigned slo = __reduce_add_sync(0xffffffffu, mine ? (unsigned)(v & 0xFFFFFu) : 0u);
-          const unsigned shi = __reduce_add_sync(0xffffffffu, mine ? (unsigned)(v >> 20) : 0u);
-          if (lane == leader) sum[l] += ((unsigned long long)shi << 20) + slo;
-        }
-        if (lane == leader) cnt[l] += (unsigned)__popc(grp);
-        todo &= ~grp;
+      const int key = inb ? label : 0x7fffffff;                // out-of-image lanes: a group of their own, not counted
+      const unsigned grp = __match_any_sync(0xffffffffu, key);
+      // v < 2^36: split so that 32 addends cannot overflow 32 bits
+      const unsigned slo = __reduce_add_sync(grp, (unsigned)(v & 0xFFFFFu));
+      const unsigned shi = __reduce_add_sync(grp, (unsigned)(v >> 20));
+      if (inb && (grp & lanemask_lt()) == 0u) {
+        cnt[label] += (unsigned)__popc(grp);
+        if (label >= 2) sum[label] += ((unsigned long long)shi << 20) + slo;
       }
       __syncwarp();
     }

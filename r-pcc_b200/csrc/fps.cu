@@ -24,6 +24,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace rpcc {
@@ -405,6 +407,7 @@ segment_fps_pruned_kernel(const float* __restrict__ range, const float* __restri
     // seed 0 is flat index 0 (sampling_gpu.cu:44-46)
     float x1, y1, z1;
     masked_point(rg[0], lut, g0, g1, g2, g3, gnorm, thr, x1, y1, z1);
+    const bool seed0_origin = (x1 == 0.f) && (y1 == 0.f) && (z1 == 0.f);
     if (tid == 0) {
       center_idx[(size_t)f * m] = 0;
       float* c = centers + (size_t)f * m * 3;
@@ -429,17 +432,35 @@ segment_fps_pruned_kernel(const float* __restrict__ range, const float* __restri
         if (inb) temp[p] = __float_as_uint(tv) | (origin ? 0x80000000u : 0u);
         const unsigned nb = inb ? __float_as_uint(tv) : 0u;
         const unsigned newmax = __reduce_max_sync(0xffffffffu, nb);
+        // A bucket whose running distances are all zero -- ground and empty pixels when seed 0 is one of them, about half
+        // of a frame's buckets -- can never change, and can only be chosen when every point of the frame sits at zero, in
+        // which case the reference's tie rule picks pixel 0 (tie key 0): bucket 0 is always kept, the others keep the
+        // defaults (maximum 0, no tie key, empty box).
+        if (newmax == 0u && b != 0) continue;                   // warp-uniform
         const unsigned tk = (inb && nb == newmax) ? ((__brev((unsigned)p) & 0xFFC00000u) | ((unsigned)p >> 10)) : kNoTie;
         const unsigned ntk = __reduce_min_sync(0xffffffffu, tk);
-        // box over the points that can still change (t > 0)
+        // box over the points that can still change (t > 0).  Coordinates inside +-250 m are shifted into (0, 512), where
+        // the bit patterns order like the values (one REDUX each, no order-preserving transform); the shift rounds to
+        // 3e-5 m and the box is widened by 1e-4 m on every side, which keeps the pruning conservative.
         const bool live = inb && tv > 0.f;
-        const int big = 0x7fffffff;
-        const float a0 = ordf(__reduce_min_sync(0xffffffffu, live ? ford(x) : big));
-        const float a1 = ordf(__reduce_min_sync(0xffffffffu, live ? ford(y) : big));
-        const float a2 = ordf(__reduce_min_sync(0xffffffffu, live ? ford(z) : big));
-        const float a3 = ordf(__reduce_max_sync(0xffffffffu, live ? ford(x) : -big));
-        const float a4 = ordf(__reduce_max_sync(0xffffffffu, live ? ford(y) : -big));
-        const float a5 = ordf(__reduce_max_sync(0xffffffffu, live ? ford(z) : -big));
+        float a0, a1, a2, a3, a4, a5;
+        if (!__any_sync(0xffffffffu, live && !(fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) < 250.f))) {
+          const unsigned ux = __float_as_uint(x + 256.f), uy = __float_as_uint(y + 256.f), uz = __float_as_uint(z + 256.f);
+          a0 = __uint_as_float(__reduce_min_sync(0xffffffffu, live ? ux : 0x7f800000u)) - 256.0001f;
+          a1 = __uint_as_float(__reduce_min_sync(0xffffffffu, live ? uy : 0x7f800000u)) - 256.0001f;
+          a2 = __uint_as_float(__reduce_min_sync(0xffffffffu, live ? uz : 0x7f800000u)) - 256.0001f;
+          a3 = __uint_as_float(__reduce_max_sync(0xffffffffu, live ? ux : 0u)) - 255.9999f;
+          a4 = __uint_as_float(__reduce_max_sync(0xffffffffu, live ? uy : 0u)) - 255.9999f;
+          a5 = __uint_as_float(__reduce_max_sync(0xffffffffu, live ? uz : 0u)) - 255.9999f;
+        } else {                                               // coordinates beyond any lidar's range (or NaN): exact order
+          const int big = 0x7fffffff;
+          a0 = ordf(__reduce_min_sync(0xffffffffu, live ? ford(x) : big));
+          a1 = ordf(__reduce_min_sync(0xffffffffu, live ? ford(y) : big));
+          a2 = ordf(__reduce_min_sync(0xffffffffu, live ? ford(z) : big));
+          a3 = ordf(__reduce_max_sync(0xffffffffu, live ? ford(x) : -big));
+          a4 = ordf(__reduce_max_sync(0xffffffffu, live ? ford(y) : -big));
+          a5 = ordf(__reduce_max_sync(0xffffffffu, live ? ford(z) : -big));
+        }
         if (lane == t) { bmax[q] = newmax; btk[q] = ntk; mx0 = a0; my0 = a1; mz0 = a2; mx1 = a3; my1 = a4; mz1 = a5; }
       }
       // an all-dead / missing bucket keeps (+big, -big): its lower bound is huge and its maximum 0
@@ -495,34 +516,42 @@ segment_fps_pruned_kernel(const float* __restrict__ range, const float* __restri
         const float lb = __fmaf_rn(oz, oz, __fmaf_rn(oy, oy, ox * ox));
         act[q] = __ballot_sync(0xffffffffu, lb * 0.99999f < __uint_as_float(bmax[q]));
       }
-      // ---- update them with the reference arithmetic
+      // ---- update them with the reference arithmetic.  When seed 0 is an origin point (a ground or empty pixel 0: the
+      //      usual case) every origin point sits at t = 0 for good -- min(d, 0) = 0 whatever coordinates go in -- so
+      //      the masked points need not be re-zeroed (SIMPLE); otherwise their origin bit decides.
+      auto update = [&](auto simple) {
 #pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        unsigned a = act[q];
-        while (a) {
-          const int t = __ffs(a) - 1;
-          a &= a - 1;
-          const int b = warp + NW * (q * 32 + t);
-          const int p = (b << 5) + lane;
-          const bool inb = p < HW;
-          unsigned nb = 0u;
-          if (inb) {
-            const unsigned tb = temp[p];
-            const float r = __ldg(rg + p);
-            const float lx = __ldg(lut + (size_t)p * 3), ly = __ldg(lut + (size_t)p * 3 + 1), lz = __ldg(lut + (size_t)p * 3 + 2);
-            const bool org = (tb >> 31) != 0u;
-            const float x = org ? 0.f : r * lx, y = org ? 0.f : r * ly, z = org ? 0.f : r * lz;
-            const float told = __uint_as_float(tb & 0x7fffffffu);
-            const float tn = fminf(fps_dist(x, y, z, x1, y1, z1), told);          // sampling_gpu.cu:64-66
-            nb = __float_as_uint(tn);
-            if (tn != told) temp[p] = nb | (tb & 0x80000000u);
+        for (int q = 0; q < Q; ++q) {
+          unsigned a = act[q];
+          while (a) {
+            const int t = __ffs(a) - 1;
+            a &= a - 1;
+            const int b = warp + NW * (q * 32 + t);
+            const int p = (b << 5) + lane;
+            const bool inb = p < HW;
+            unsigned nb = 0u;
+            if (inb) {
+              const unsigned tb = temp[p];
+              const float r = __ldg(rg + p);
+              const float lx = __ldg(lut + (size_t)p * 3), ly = __ldg(lut + (size_t)p * 3 + 1), lz = __ldg(lut + (size_t)p * 3 + 2);
+              float x = r * lx, y = r * ly, z = r * lz;
+              if (!decltype(simple)::value) {
+                const bool org = (tb >> 31) != 0u;
+                x = org ? 0.f : x; y = org ? 0.f : y; z = org ? 0.f : z;
+              }
+              const float told = __uint_as_float(tb & 0x7fffffffu);
+              const float tn = fminf(fps_dist(x, y, z, x1, y1, z1), told);          // sampling_gpu.cu:64-66
+              nb = __float_as_uint(tn);
+              if (tn != told) temp[p] = nb | (tb & 0x80000000u);
+            }
+            const unsigned newmax = __reduce_max_sync(0xffffffffu, nb);
+            const unsigned tk = (inb && nb == newmax) ? ((__brev((unsigned)p) & 0xFFC00000u) | ((unsigned)p >> 10)) : kNoTie;
+            const unsigned ntk = __reduce_min_sync(0xffffffffu, tk);
+            if (lane == t) { bmax[q] = newmax; btk[q] = ntk; }
           }
-          const unsigned newmax = __reduce_max_sync(0xffffffffu, nb);
-          const unsigned tk = (inb && nb == newmax) ? ((__brev((unsigned)p) & 0xFFC00000u) | ((unsigned)p >> 10)) : kNoTie;
-          const unsigned ntk = __reduce_min_sync(0xffffffffu, tk);
-          if (lane == t) { bmax[q] = newmax; btk[q] = ntk; }
         }
-      }
+      };
+      if (seed0_origin) update(std::true_type()); else update(std::false_type());
     }
     __syncthreads();   // the next frame's first pass rewrites temp[], s_part and s_frame
   }

@@ -232,6 +232,30 @@ def test_segment_fps_and_labels(T, R, lidar):
         assert np.array_equal(labels[b].cpu().numpy().astype(np.int64), seg_t), (lidar, b)
 
 
+def test_segment_fps_when_seed_zero_is_a_real_point(T, R):
+    """The FPS kernel has two update paths: the usual one (pixel 0 is a ground / empty pixel, so every masked point sits
+    at distance zero from seed 0 for good) and the general one, taken when pixel 0 survives the ground mask -- then the
+    masked points are live candidates, tie among themselves across the whole image, and can be chosen.  A ground model
+    far from every point masks nothing; the empty pixels still are origin points."""
+    import refimpl
+    lidar = "VelodyneVLP16"
+    pts, off, grounds = _frames(R, lidar, [7, 8])
+    cfg, rng = _project_dev(T, R, pts, off, lidar)
+    lut = cfg.transform_map()
+    ri = rng.cpu().numpy()
+    assert (ri[:, 0, 0] != 0).all()                     # pixel 0 holds a point in these frames
+    g = np.tile(np.array([[0.0, 0.0, 1.0, 100.0]], np.float32), (2, 1))
+    d_lut, d_g = T.from_numpy(lut).cuda(), T.from_numpy(g).cuda()
+    cidx, centers = R.device_mod.segment_fps_batch(rng, d_lut, d_g, 100, 0.1)
+    labels, _ = R.device_mod.assign_labels_batch(rng, d_lut, d_g, centers)
+    T.cuda.synchronize()
+    for b in range(2):
+        seg_t, cidx_t, ng_t = refimpl.torch_segment(ri[b], lut, g[b], 100)
+        assert np.array_equal(cidx[b].cpu().numpy(), cidx_t), b
+        assert np.array_equal(centers[b].cpu().numpy(), ng_t[cidx_t]), b
+        assert np.array_equal(labels[b].cpu().numpy().astype(np.int64), seg_t), b
+
+
 def test_segment_example_frame(T, R, example_points):
     import refimpl
     off = np.array([0, example_points.shape[0]], np.int64)
