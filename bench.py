@@ -50,9 +50,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=2368, help="frames resident on each GPU (default 2 x 1184)")
-    ap.add_argument("--passes", type=int, default=4,
-                    help="passes over the resident frames per step (4 x 2368 frames = ~100 ms per step: a 20-step run "
-                         "is a 2 s timed region)")
+    ap.add_argument("--passes", type=int, default=10,
+                    help="passes over the resident frames per step (10 x 2368 frames = ~120 ms per step: a 20-step run "
+                         "is a 2.4 s timed region)")
     ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic frames generated per GPU")
     ap.add_argument("--max-batch", type=int, default=1184,
                     help="frames per kernel launch (8 x 148 SMs: the one-CTA-per-frame kernels draw frames from a queue, "
