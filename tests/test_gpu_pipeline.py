@@ -285,6 +285,32 @@ def test_encoder_device_path_and_ground_fit(R):
             assert symbols[sym_base[b]:sym_base[b + 1]].tobytes() == want["sections"]["residual_quantized"]
 
 
+def test_degenerate_frames_in_a_batch(R):
+    """An empty frame, a five-point frame and a frame whose points all lie on the ground (every pixel masked: FPS runs on
+    a cloud of identical origin points and the tie rule alone picks the seeds) between two ordinary frames: every section
+    equals the oracle's, and the streams decode."""
+    from rpcc_b200 import synthetic
+    from rpcc_b200.batch import BatchDecoder, BatchEncoder
+    lidar = "VelodyneVLP16"
+    a, ga = synthetic.frame(90, lidar)
+    b, gb = synthetic.frame(91, lidar)
+    flat = a[np.abs(a[:, :3] @ ga[:3] + ga[3]) < 0.05][:4000]          # ground returns only
+    frames = [a, np.zeros((0, 4), np.float32), b[:5].copy(), flat, b]
+    grounds = np.stack([ga, ga, gb, ga, gb])
+    pts = np.concatenate(frames, 0)
+    off = np.cumsum([0] + [f.shape[0] for f in frames]).astype(np.int64)
+    with BatchEncoder(lidar, accuracy=0.02, max_batch=8, max_points=max(pts.shape[0], 1), host_chunk=2) as enc:
+        out = enc.encode_host(pts, off, grounds)
+        for i, f in enumerate(frames):
+            want = oracle.compress_frame(f, lidar, grounds[i])["sections"]
+            got = BatchEncoder.frame_sections(out, i)
+            for k in want:
+                assert got[k] == want[k], (i, k)
+        blobs = enc.compress(pts, off, grounds)
+    d = BatchDecoder(lidar, accuracy=0.02).decode(blobs, want_xyz=False, want_points=True)
+    assert d["points"][1].shape[0] == 0 and d["points"][2].shape[0] <= 5 and d["points"][0].shape[0] > 10000
+
+
 def test_encode_host_is_independent_of_the_pipeline_chunking(R):
     """encode_host cuts a call into host_chunk-frame pipeline stages; every section (including the ground
     plane fitted on the device, keyed by the frame's index within the call) must not depend on the cut."""
