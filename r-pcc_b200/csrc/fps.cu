@@ -372,8 +372,8 @@ static int launch_segment_fps(const float* range, const float* lut, const float*
 //   state in global memory (L2-resident): t[HW] per CTA, bit 31 = "masked to the origin"
 //   state on chip: boxes in shared memory (6 floats per bucket), max t / tie key in registers.
 constexpr unsigned kNoTie = 0xFFFFFFFFu;
-#ifndef RPCC_FPS_WF
-#define RPCC_FPS_WF 1
+#ifndef RPCC_FPS_ONEWINNER
+#define RPCC_FPS_ONEWINNER 1
 #endif
 
 __device__ __forceinline__ int ford(float f) { const int b = __float_as_int(f); return b ^ ((b >> 31) & 0x7fffffff); }
@@ -390,6 +390,7 @@ segment_fps_pruned_kernel(const float* __restrict__ range, const float* __restri
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_box = reinterpret_cast<float*>(smem_raw);            // [6][Q][THREADS]: x0,y0,z0,x1,y1,z1 of bucket (q, tid)
   __shared__ uint2 s_part[2][32];
+  __shared__ float4 s_win[2];
   __shared__ int s_frame;
   unsigned* temp = temp_ws + (size_t)blockIdx.x * HW;
   const float INF = __int_as_float(0x7f800000);
@@ -483,26 +484,43 @@ segment_fps_pruned_kernel(const float* __restrict__ range, const float* __restri
         const unsigned tw = __reduce_min_sync(0xffffffffu, d == dw ? tk : kNoTie);
         if (lane == 0) s_part[j & 1][warp] = make_uint2(dw, tw);
         __syncthreads();
+#if RPCC_FPS_ONEWINNER
+        // warp 0 alone reduces the warps' winners, fetches the centre and publishes it: a second block sync, but 31 warps
+        // skip ~30 instructions a round
+        if (warp == 0) {
+          const uint2 v = lane < NW ? s_part[j & 1][lane] : make_uint2(0u, kNoTie);
+          const unsigned dmax = __reduce_max_sync(0xffffffffu, v.x);
+          const unsigned tkmin = __reduce_min_sync(0xffffffffu, v.x == dmax ? v.y : kNoTie);
+          const int k = (int)(((tkmin & 0x3FFFFFu) << 10) | __brev(tkmin & 0xFFC00000u));
+          if (lane == 0) {
+            const float r = ld_stream_f(rg + k);
+            const float wx = ld_stream_f(lut + (size_t)k * 3), wy = ld_stream_f(lut + (size_t)k * 3 + 1), wz = ld_stream_f(lut + (size_t)k * 3 + 2);
+            const bool org = (temp[k] >> 31) != 0u;
+            const float cx = org ? 0.f : r * wx, cy = org ? 0.f : r * wy, cz = org ? 0.f : r * wz;
+            s_win[j & 1] = make_float4(cx, cy, cz, 0.f);
+            center_idx[(size_t)f * m + j] = k;
+            float* c = centers + ((size_t)f * m + j) * 3;
+            c[0] = cx; c[1] = cy; c[2] = cz;
+          }
+        }
+        __syncthreads();
+        { const float4 w = s_win[j & 1]; x1 = w.x; y1 = w.y; z1 = w.z; }
+#else
         const uint2 v = lane < NW ? s_part[j & 1][lane] : make_uint2(0u, kNoTie);
         const unsigned dmax = __reduce_max_sync(0xffffffffu, v.x);
         const unsigned tkmin = __reduce_min_sync(0xffffffffu, v.x == dmax ? v.y : kNoTie);
         const int k = (int)(((tkmin & 0x3FFFFFu) << 10) | __brev(tkmin & 0xFFC00000u));
-#if RPCC_FPS_WF
         // all five loads leave together (volatile asm: the compiler would otherwise predicate the last four on the first)
         const float r = ld_stream_f(rg + k);
         const float wx = ld_stream_f(lut + (size_t)k * 3), wy = ld_stream_f(lut + (size_t)k * 3 + 1), wz = ld_stream_f(lut + (size_t)k * 3 + 2);
         const bool org = (temp[k] >> 31) != 0u;
         x1 = org ? 0.f : r * wx; y1 = org ? 0.f : r * wy; z1 = org ? 0.f : r * wz;
-#else
-        const bool org = (temp[k] >> 31) != 0u;
-        const float r = rg[k];
-        x1 = org ? 0.f : r * lut[(size_t)k * 3]; y1 = org ? 0.f : r * lut[(size_t)k * 3 + 1]; z1 = org ? 0.f : r * lut[(size_t)k * 3 + 2];
-#endif
         if (tid == 0) {
           center_idx[(size_t)f * m + j] = k;
           float* c = centers + ((size_t)f * m + j) * 3;
           c[0] = x1; c[1] = y1; c[2] = z1;
         }
+#endif
       }
       if (j == m - 1) break;                                  // the last centre needs no update pass
       // ---- which of my buckets can change?
