@@ -134,11 +134,17 @@ assign_labels_kernel(const float* __restrict__ range, const float* __restrict__ 
     const bool valid = inb && r != 0.0f;
     const float maxb = __uint_as_float(__reduce_max_sync(0xffffffffu, valid ? __float_as_uint(best) : 0u));
     if (__any_sync(0xffffffffu, valid) && !(maxb < skip_thr)) {
-      // bounding sphere of the slice's valid points: box centre, farthest valid point
-      const int big = 0x7fffffff;
-      const float ox = 0.5f * (ord2f(__reduce_min_sync(0xffffffffu, valid ? f2ord(x) : big)) + ord2f(__reduce_max_sync(0xffffffffu, valid ? f2ord(x) : -big)));
-      const float oy = 0.5f * (ord2f(__reduce_min_sync(0xffffffffu, valid ? f2ord(y) : big)) + ord2f(__reduce_max_sync(0xffffffffu, valid ? f2ord(y) : -big)));
-      const float oz = 0.5f * (ord2f(__reduce_min_sync(0xffffffffu, valid ? f2ord(z) : big)) + ord2f(__reduce_max_sync(0xffffffffu, valid ? f2ord(z) : -big)));
+      // bounding sphere of the slice's valid points: box centre, farthest valid point.  Any centre will do -- the radius
+      // below is taken from the points themselves -- so the box comes from coordinates shifted by +256 m, whose bit
+      // patterns order like the values for anything a lidar returns (one REDUX per face, no order-preserving transform);
+      // beyond that range the centre is merely a poor one and the sphere a large one.
+      const unsigned ux = __float_as_uint(x + 256.f), uy = __float_as_uint(y + 256.f), uz = __float_as_uint(z + 256.f);
+      const float ox = __fmaf_rn(0.5f, __uint_as_float(__reduce_min_sync(0xffffffffu, valid ? ux : 0x7f7fffffu)) +
+                                       __uint_as_float(__reduce_max_sync(0xffffffffu, valid ? ux : 0u)), -256.f);
+      const float oy = __fmaf_rn(0.5f, __uint_as_float(__reduce_min_sync(0xffffffffu, valid ? uy : 0x7f7fffffu)) +
+                                       __uint_as_float(__reduce_max_sync(0xffffffffu, valid ? uy : 0u)), -256.f);
+      const float oz = __fmaf_rn(0.5f, __uint_as_float(__reduce_min_sync(0xffffffffu, valid ? uz : 0x7f7fffffu)) +
+                                       __uint_as_float(__reduce_max_sync(0xffffffffu, valid ? uz : 0u)), -256.f);
       const float ex = x - ox, ey = y - oy, ez = z - oz;
       const float e2 = valid ? __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, ex * ex)) : 0.f;
       // (bounds only: the approximate square root's 2 ulp disappear in the 1e-5 slack)

@@ -388,7 +388,8 @@ segment_fps_pruned_kernel(const float* __restrict__ range, const float* __restri
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int NB = (HW + 31) >> 5;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* s_box = reinterpret_cast<float*>(smem_raw);            // [6][Q][THREADS]: x0,y0,z0,x1,y1,z1 of bucket (q, tid)
+  float4* s_boxa = reinterpret_cast<float4*>(smem_raw);          // [Q][THREADS]: x0, y0, z0, x1 of bucket (q, tid)
+  float2* s_boxb = reinterpret_cast<float2*>(s_boxa + Q * THREADS);   // [Q][THREADS]: y1, z1
   __shared__ uint2 s_part[2][32];
   __shared__ float4 s_win[2];
   __shared__ int s_frame;
@@ -465,9 +466,8 @@ segment_fps_pruned_kernel(const float* __restrict__ range, const float* __restri
         if (lane == t) { bmax[q] = newmax; btk[q] = ntk; mx0 = a0; my0 = a1; mz0 = a2; mx1 = a3; my1 = a4; mz1 = a5; }
       }
       // an all-dead / missing bucket keeps (+big, -big): its lower bound is huge and its maximum 0
-      float* bx = s_box + q * THREADS + tid;
-      bx[0] = mx0; bx[Q * THREADS] = my0; bx[2 * Q * THREADS] = mz0;
-      bx[3 * Q * THREADS] = mx1; bx[4 * Q * THREADS] = my1; bx[5 * Q * THREADS] = mz1;
+      s_boxa[q * THREADS + tid] = make_float4(mx0, my0, mz0, mx1);
+      s_boxb[q * THREADS + tid] = make_float2(my1, mz1);
     }
     // (boxes are private to their owner thread: no synchronisation needed before they are read back)
 
@@ -527,10 +527,11 @@ segment_fps_pruned_kernel(const float* __restrict__ range, const float* __restri
       unsigned act[Q];
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
-        const float* bx = s_box + q * THREADS + tid;
-        const float ox = fmaxf(fmaxf(bx[0] - x1, x1 - bx[3 * Q * THREADS]), 0.f);
-        const float oy = fmaxf(fmaxf(bx[Q * THREADS] - y1, y1 - bx[4 * Q * THREADS]), 0.f);
-        const float oz = fmaxf(fmaxf(bx[2 * Q * THREADS] - z1, z1 - bx[5 * Q * THREADS]), 0.f);
+        const float4 ba = s_boxa[q * THREADS + tid];            // two vector loads per box (six scalar ones before)
+        const float2 bb = s_boxb[q * THREADS + tid];
+        const float ox = fmaxf(fmaxf(ba.x - x1, x1 - ba.w), 0.f);
+        const float oy = fmaxf(fmaxf(ba.y - y1, y1 - bb.x), 0.f);
+        const float oz = fmaxf(fmaxf(ba.z - z1, z1 - bb.y), 0.f);
         const float lb = __fmaf_rn(oz, oz, __fmaf_rn(oy, oy, ox * ox));
         act[q] = __ballot_sync(0xffffffffu, lb * 0.99999f < __uint_as_float(bmax[q]));
       }
