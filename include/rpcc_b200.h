@@ -363,8 +363,9 @@ RPCC_API void* rpcc_encoder_device_buffer(rpcc_encoder* enc, int slot, const cha
 /* The host side of tools/compress_datalist.py:91-141 as native threads: BasicCompressor.compress_dict +
  * save_compressed_bitstream (utils/compress_utils.py:167-179,255-310) for every frame of an encode_host call, on a
  * persistent pool, straight out of the caller's pinned output buffers.  Only method "bzip2" (the reference default,
- * cfgs/compressor.yaml:2; the system libbz2 at level 9 -- the bytes CPython's bz2.compress writes); deflate / lz4 stay
- * on the Python pool. */
+ * cfgs/compressor.yaml:2; level 9 -- the bytes CPython's bz2.compress writes); deflate / lz4 stay on the Python pool.
+ * Two coders produce those bytes, the system libbz2 and rpcc_bz2_compress; every worker measures both per section and
+ * uses the cheaper one (environment RPCC_BZ2_CODER = auto | libbz2 | own). */
 typedef struct rpcc_packer rpcc_packer;
 RPCC_API int rpcc_packer_create(int threads, const char* method, rpcc_packer** out);
 RPCC_API void rpcc_packer_destroy(rpcc_packer* pk);
@@ -377,6 +378,11 @@ RPCC_API int rpcc_packer_submit(rpcc_packer* pk, int B, int K, int cbytes, int u
                        const uint8_t* salience, const char* const* paths, uint32_t* bytes_out, int* status_out,
                        uint8_t* blobs, size_t blob_stride, long long* ticket_out);
 RPCC_API int rpcc_packer_wait(rpcc_packer* pk, long long ticket);
+/* bz2.compress(src) (utils/compress_utils.py:296-298: bzip2, level 9) by this library's own encoder (bz2enc.cu: the same
+ * bitstream as libbz2, rotations sorted by induced sorting).  Returns RPCC_OK, RPCC_BZ2_DECLINED (1: input this encoder
+ * leaves to libbz2 -- more than one block, or a block made of repetitions of a shorter string) or RPCC_ERR_CAPACITY. */
+#define RPCC_BZ2_DECLINED 1
+RPCC_API int rpcc_bz2_compress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_len);
 /* dataset/dataset.py:57-63 for a KITTI .bin (rows of x,y,z,intensity f32): the xyz columns into dst (room for
  * cap_rows rows of 3 floats, typically a slice of the pinned upload buffer); *rows_out = rows in the file. */
 RPCC_API int rpcc_read_bin_xyz(const char* path, float* dst, int64_t cap_rows, int64_t* rows_out);

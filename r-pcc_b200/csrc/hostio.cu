@@ -4,17 +4,20 @@
 //
 // The reference does both per frame under the GIL: np.fromfile + a slice (dataset/dataset.py:57-70) and
 // BasicCompressor.compress_dict + save_compressed_bitstream (utils/compress_utils.py:167-179,255-310) inside the
-// ThreadPoolExecutor closure of tools/compress_datalist.py:91-141.  The coder itself is unchanged -- the sequential
-// bzip2 of the system's own libbz2 (the library CPython's bz2 module links), level 9 -- so the bytes are the
-// reference's; what changes is that no Python runs per frame, and that the pool works on batch k out of one set of
-// pinned buffers while the GPU fills the other set with batch k+1.
+// ThreadPoolExecutor closure of tools/compress_datalist.py:91-141.  The format is unchanged -- bzip2 level 9, byte for
+// byte what the system's libbz2 (the library CPython's bz2 module links) writes, whether libbz2 itself or this
+// library's encoder (bz2enc.cu) produced it -- so the files are the reference's; what changes is that no Python runs
+// per frame, that the pool works on batch k out of one set of pinned buffers while the GPU fills the other set with
+// batch k+1, and that the slow part of libbz2 on this data (its block sort) is avoided where that pays.
 //
 // libbz2 ships without headers in this image: the two prototypes used are declared here and resolved with dlopen.
 #include <dlfcn.h>
 #include <errno.h>
 #include <fcntl.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <condition_variable>
@@ -82,14 +85,32 @@ struct rpcc_packer {
   std::deque<Job> queue;
   std::deque<Ticket> tickets;
   long long next_ticket = 1;
+  int coder = 0;             // 0 = the cheaper of the two per section (measured), 1 = libbz2, 2 = this library's encoder
   bool stop = false;
   char err[256] = "";
 };
 
 namespace {
 
+// Two coders write the same bytes: libbz2 (the call CPython's bz2.compress makes, level 9; the work factor only chooses
+// when libbz2 gives up on its main sort, never the bytes) and this library's own encoder (bz2enc.cu: induced sorting
+// instead of libbz2's block sort -- 3 to 5 times faster on label sequences, on a par on noisy residuals, behind on
+// small inputs).  Which one is faster depends on the section and on the data, so every worker keeps, per section of the
+// file, a running cost per byte of both and uses the cheaper one, probing the other now and then.  mode: 0 = that,
+// 1 = libbz2 only, 2 = own encoder (libbz2 where it declines).
+struct CoderStats {
+  double cost[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};   // ns per byte, [coder][section slot]
+  unsigned seen[5] = {0, 0, 0, 0, 0};
+};
+
+inline double now_ns() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return 1e9 * (double)ts.tv_sec + (double)ts.tv_nsec;
+}
+
 // `.rpcc` = per section [int32 length][entropy-coded bytes] (utils/compress_utils.py:167-179)
-int pack_one(const Bz2* bz, const Job& j, std::vector<unsigned char>& out, std::vector<char>& tmp) {
+int pack_one(const Bz2* bz, const Job& j, std::vector<unsigned char>& out, std::vector<char>& tmp, CoderStats& st, int mode) {
   out.clear();
   for (int s = 0; s < j.nsec; ++s) {
     const size_t n = j.len[s];
@@ -97,10 +118,36 @@ int pack_one(const Bz2* bz, const Job& j, std::vector<unsigned char>& out, std::
     unsigned cap = (unsigned)(n + n / 100 + 600);    // bzlib manual: 1 % + 600 bytes always suffices
     if (tmp.size() < cap) tmp.resize(cap);
     unsigned got = cap;
-    // the same call CPython's bz2.compress makes section by section (level 9); the work factor only chooses when
-    // libbz2 gives up on its main sort and falls back, never the bytes (bzip2 manual, BZ2_bzCompressInit)
-    const int rc = bz->compress(tmp.data(), &got, reinterpret_cast<char*>(const_cast<unsigned char*>(j.sec[s])), (unsigned)n, 9, 0, j.wf[s]);
+    const int slot = s + (5 - j.nsec);               // the last four sections line up whether or not salience leads
+    int use = mode == 1 ? 1 : 0;                     // 0 = own, 1 = libbz2
+    if (mode == 0) {
+      const unsigned k = st.seen[slot]++;
+      if (k == 0) use = 0;
+      else if (k == 1) use = 1;
+      else {
+        use = st.cost[1][slot] < st.cost[0][slot] ? 1 : 0;
+        if ((k & 127u) == 0) use ^= 1;               // the other one gets a turn: the data may have changed
+      }
+    }
+    const double t0 = now_ns();
+    int rc = RPCC_BZ2_DECLINED;
+    if (use == 0) {
+      size_t got2 = 0;
+      rc = rpcc_bz2_compress(j.sec[s], n, reinterpret_cast<uint8_t*>(tmp.data()), cap, &got2);
+      got = (unsigned)got2;
+      if (rc != RPCC_OK && rc != RPCC_BZ2_DECLINED) return rc;
+    }
+    if (rc == RPCC_BZ2_DECLINED) {
+      use = 1;
+      got = cap;
+      rc = bz->compress(tmp.data(), &got, reinterpret_cast<char*>(const_cast<unsigned char*>(j.sec[s])), (unsigned)n, 9, 0, j.wf[s]);
+    }
     if (rc != 0) return RPCC_ERR_ARG;
+    if (n >= 512) {                                  // (tiny sections say nothing about either coder)
+      const double c = (now_ns() - t0) / (double)n;
+      double& e = st.cost[use][slot];
+      e = e == 0 ? c : 0.75 * e + 0.25 * c;
+    }
     const int32_t len32 = (int32_t)got;
     const size_t at = out.size();
     out.resize(at + 4 + got);
@@ -126,6 +173,7 @@ void worker(rpcc_packer* pk) {
   const Bz2* bz = bz2lib();
   std::vector<unsigned char> out;
   std::vector<char> tmp;
+  CoderStats stats;
   for (;;) {
     Job j;
     {
@@ -135,7 +183,7 @@ void worker(rpcc_packer* pk) {
       j = std::move(pk->queue.front());
       pk->queue.pop_front();
     }
-    int rc = bz ? pack_one(bz, j, out, tmp) : RPCC_ERR_ARG;
+    int rc = bz ? pack_one(bz, j, out, tmp, stats, pk->coder) : RPCC_ERR_ARG;
     if (rc == RPCC_OK) {
       if (j.bytes_out) *j.bytes_out = (uint32_t)out.size();
       if (j.blob) {
@@ -174,6 +222,7 @@ extern "C" int rpcc_packer_create(int threads, const char* method, rpcc_packer**
   if (!bz2lib()) { set_error("rpcc_packer_create: libbz2.so.1.0 could not be loaded"); return RPCC_ERR_ARG; }
   rpcc_packer* pk = new (std::nothrow) rpcc_packer();
   RPCC_REQUIRE(pk != nullptr, "out of host memory");
+  if (const char* e = getenv("RPCC_BZ2_CODER")) pk->coder = !strcmp(e, "libbz2") ? 1 : !strcmp(e, "own") ? 2 : 0;
   for (int i = 0; i < threads; ++i) pk->threads.emplace_back(worker, pk);
   *out = pk;
   return RPCC_OK;

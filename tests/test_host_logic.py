@@ -206,3 +206,84 @@ def test_native_packer_writes_the_bytes_python_bz2_would(tmp_path):
     assert np.array_equal(dst[:frames[0][0].shape[0]], frames[0][0][:, :3])
     with pytest.raises(Exception):
         read_bin_xyz(str(f), dst[:10])
+
+
+def _own_bz2(raw):
+    import ctypes as C
+    import rpcc_b200
+    raw = bytes(raw)
+    cap = len(raw) + len(raw) // 100 + 700
+    dst = C.create_string_buffer(cap)
+    n = C.c_size_t(0)
+    rc = rpcc_b200.lib().rpcc_bz2_compress(raw, C.c_size_t(len(raw)), dst, C.c_size_t(cap), C.byref(n))
+    return rc, dst.raw[:n.value]
+
+
+def test_own_bzip2_encoder_writes_libbz2_bytes():
+    """csrc/bz2enc.cu must write exactly what bz2.compress (libbz2, level 9) writes -- the reference's coder,
+    utils/compress_utils.py:296-298 -- or decline (1): edge cases of the run-length pass and of the table-count thresholds,
+    random / low-entropy / int16 / run-heavy inputs of many sizes, every section of real frames, and the inputs it must
+    leave to libbz2 (blocks that repeat a shorter string, more than one block)."""
+    import bz2
+    from rpcc_b200 import synthetic
+    rng = np.random.default_rng(11)
+    cases = [b"", b"a", b"ab", b"abc", b"aaaa", b"aaaab", b"aaaaa" * 3 + b"b", b"abracadabra", bytes(range(256)),
+             bytes(range(256)) * 3 + b"x", b"\x00" * 70000 + b"\x01"]
+    for L in (3, 4, 5, 254, 255, 256, 258, 259, 260, 510, 511, 600, 1020):
+        cases.append(b"x" * L + b"y")
+        cases.append(b"y" + b"x" * L)
+    for n in (5, 50, 199, 200, 201, 599, 600, 1199, 1200, 2399, 2400, 10000, 70000):     # nMTF thresholds: 200/600/1200/2400
+        cases.append(rng.integers(0, 256, n).astype(np.uint8).tobytes())
+        cases.append(rng.integers(0, 3, n).astype(np.uint8).tobytes())
+        cases.append(rng.integers(-30, 30, n // 2 + 1).astype(np.int16).tobytes())
+        cases.append(np.repeat(rng.integers(0, 100, n // 7 + 1), rng.integers(1, 600, n // 7 + 1)).astype(np.uint8).tobytes()[:n])
+        cases.append(rng.integers(0, 102, n // 2 + 1).astype(np.uint16).tobytes())
+    for lidar in ("Velodyne64E", "VelodyneVLP16"):
+        for nu in (False, True):
+            p, g = synthetic.frame(5, lidar)
+            cases.extend(oracle.compress_frame(p, lidar, g, nonuniform=nu)["sections"].values())
+    done = 0
+    for c in cases:
+        rc, out = _own_bz2(c)
+        assert rc in (0, 1), rc
+        if rc == 0:
+            assert out == bz2.compress(bytes(c)), (len(c), bytes(c[:16]))
+            done += 1
+    assert done >= len(cases) - 2
+    # declined: whole repetitions of a shorter string (identical rotations: libbz2's order among them is its own), two blocks
+    assert _own_bz2(b"abcabcabc")[0] == 1 and _own_bz2(b"ab" * 5000)[0] == 1
+    assert _own_bz2(bytes(1020))[0] == 1                    # 4 x 255 zeros: the run-length pass makes a period of five of them
+    assert _own_bz2(bytes(1000))[0] == 0 and _own_bz2(bytes(1000))[1] == bz2.compress(bytes(1000))
+    assert _own_bz2(rng.integers(0, 256, 950000).astype(np.uint8).tobytes())[0] == 1
+
+
+@pytest.mark.parametrize("coder", ["auto", "own", "libbz2"])
+def test_packer_coders_agree(tmp_path, monkeypatch, coder):
+    """The entropy pool may use libbz2, the library's own encoder, or whichever it measures as cheaper per section: the
+    files are the same."""
+    from rpcc_b200 import synthetic
+    from rpcc_b200.batch import RESULT_DTYPE
+    from rpcc_b200.hostio import Packer
+    monkeypatch.setenv("RPCC_BZ2_CODER", coder)
+    B, K = 6, 102
+    secs = []
+    for i in range(B):
+        p, g = synthetic.frame(80 + i % 3, "VelodyneVLP16")
+        secs.append(oracle.compress_frame(p, "VelodyneVLP16", g)["sections"])
+    cb = len(secs[0]["contour_map"])
+    res = np.zeros(B, RESULT_DTYPE)
+    model, contour = np.zeros((B, K, 4), np.float32), np.zeros((B, cb), np.uint8)
+    seq, sym = [], []
+    for b, s in enumerate(secs):
+        rows = len(s["plane_param"]) // 16
+        res[b] = (len(s["residual_quantized"]) // 2, len(s["idx_sequence"]) // 2, rows, 0)
+        model[b, :rows] = np.frombuffer(s["plane_param"], np.float32).reshape(-1, 4)
+        contour[b] = np.frombuffer(s["contour_map"], np.uint8)
+        seq.append(np.frombuffer(s["idx_sequence"], np.uint16))
+        sym.append(np.frombuffer(s["residual_quantized"], np.int16))
+    enc = dict(results=res, model=model, contour=contour, seq=np.concatenate(seq), symbols=np.concatenate(sym), salience=None)
+    pk = Packer(1, "bzip2")                                  # one worker: frames 0, 1, 2.. go through the probing sequence
+    sizes, blobs = pk.wait(pk.submit(enc, K, True, None, keep=True))
+    pk.close()
+    for b in range(B):
+        assert blobs[b, :sizes[b]].tobytes() == oracle.write_rpcc(secs[b]), (coder, b)
