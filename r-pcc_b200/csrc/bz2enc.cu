@@ -53,47 +53,61 @@ struct CrcTable {
 const CrcTable g_crc;
 
 // ------------------------------------------------------------------------------------------------ suffix sorting (SA-IS)
-// s[0..n): symbols in [0, K), s[n-1] = 0 is the unique smallest one.  SA receives the suffix array.
-// bucket boundaries from the symbol counts of the level (counted once)
+// s[0..n): symbols in [0, K), s[n-1] = 0 is the unique smallest one.  SA receives the suffix array.  The string is
+// packed in place -- symbol << 1 | type (1 = S-type, 0 = L-type) -- so that the induction passes, whose accesses into
+// the string are random, touch one array instead of two (they are what the sort spends its time on).
 inline void get_buckets(const int* cnt, int* bkt, int K, bool end) {
   int sum = 0;
   for (int i = 0; i < K; ++i) { sum += cnt[i]; bkt[i] = end ? sum : sum - cnt[i]; }
 }
 template <typename Ch>
-void induce_l(const unsigned char* t, int* SA, const Ch* s, const int* cnt, int* bkt, int n, int K) {
+void induce_l(int* SA, const Ch* s, const int* cnt, int* bkt, int n, int K) {
   get_buckets(cnt, bkt, K, false);
   for (int i = 0; i < n; ++i) {
     const int j = SA[i] - 1;
-    if (j >= 0 && !t[j]) SA[bkt[s[j]]++] = j;
+    if (j >= 0) {
+      const unsigned v = (unsigned)s[j];
+      if (!(v & 1u)) SA[bkt[v >> 1]++] = j;
+    }
   }
 }
 template <typename Ch>
-void induce_s(const unsigned char* t, int* SA, const Ch* s, const int* cnt, int* bkt, int n, int K) {
+void induce_s(int* SA, const Ch* s, const int* cnt, int* bkt, int n, int K) {
   get_buckets(cnt, bkt, K, true);
   for (int i = n - 1; i >= 0; --i) {
     const int j = SA[i] - 1;
-    if (j >= 0 && t[j]) SA[--bkt[s[j]]] = j;
+    if (j >= 0) {
+      const unsigned v = (unsigned)s[j];
+      if (v & 1u) SA[--bkt[v >> 1]] = j;
+    }
   }
 }
 template <typename Ch>
-void sais(const Ch* s, int* SA, int n, int K, std::vector<unsigned char>& tbuf, size_t toff) {
-  if (tbuf.size() < toff + (size_t)n) tbuf.resize(toff + (size_t)n);
-  unsigned char* t = tbuf.data() + toff;                    // 1 = S-type, 0 = L-type
-  t[n - 1] = 1;
-  if (n >= 2) t[n - 2] = 0;
-  for (int i = n - 3; i >= 0; --i) t[i] = (s[i] < s[i + 1] || (s[i] == s[i + 1] && t[i + 1])) ? 1 : 0;
-  auto is_lms = [&](int i) { return i > 0 && t[i] && !t[i - 1]; };
+void sais(Ch* s, int* SA, int n, int K) {
   std::vector<int> bucket((size_t)K * 2);
   int* bkt = bucket.data();
   int* cnt = bkt + K;
   for (int i = 0; i < K; ++i) cnt[i] = 0;
   for (int i = 0; i < n; ++i) ++cnt[s[i]];
+  {                                                        // types, packed into the string (back to front)
+    bool tn = true;
+    unsigned nxt = (unsigned)s[n - 1];
+    s[n - 1] = (Ch)((nxt << 1) | 1u);
+    for (int i = n - 2; i >= 0; --i) {
+      const unsigned cur = (unsigned)s[i];
+      const bool ti = cur < nxt || (cur == nxt && tn);
+      s[i] = (Ch)((cur << 1) | (ti ? 1u : 0u));
+      tn = ti;
+      nxt = cur;
+    }
+  }
+  auto is_lms = [&](int i) { return i > 0 && (s[i] & 1) && !(s[i - 1] & 1); };
   // stage 1: sort the LMS substrings
   get_buckets(cnt, bkt, K, true);
   for (int i = 0; i < n; ++i) SA[i] = -1;
-  for (int i = 1; i < n; ++i) if (t[i] && !t[i - 1]) SA[--bkt[s[i]]] = i;
-  induce_l(t, SA, s, cnt, bkt, n, K);
-  induce_s(t, SA, s, cnt, bkt, n, K);
+  for (int i = 1; i < n; ++i) if ((s[i] & 1) && !(s[i - 1] & 1)) SA[--bkt[s[i] >> 1]] = i;
+  induce_l(SA, s, cnt, bkt, n, K);
+  induce_s(SA, s, cnt, bkt, n, K);
   int n1 = 0;
   for (int i = 0; i < n; ++i) if (is_lms(SA[i])) SA[n1++] = SA[i];
   for (int i = n1; i < n; ++i) SA[i] = -1;
@@ -102,7 +116,7 @@ void sais(const Ch* s, int* SA, int n, int K, std::vector<unsigned char>& tbuf, 
     int pos = SA[i];
     bool diff = false;
     for (int d = 0; d < n; ++d) {
-      if (prev == -1 || s[pos + d] != s[prev + d] || t[pos + d] != t[prev + d]) { diff = true; break; }
+      if (prev == -1 || s[pos + d] != s[prev + d]) { diff = true; break; }       // symbol and type at once
       if (d > 0 && (is_lms(pos + d) || is_lms(prev + d))) break;
     }
     if (diff) { ++name; prev = pos; }
@@ -114,23 +128,22 @@ void sais(const Ch* s, int* SA, int n, int K, std::vector<unsigned char>& tbuf, 
   int* SA1 = SA;
   int* s1 = SA + n - n1;
   if (name < n1) {
-    sais<int>(s1, SA1, n1, name, tbuf, toff + (size_t)n);
-    t = tbuf.data() + toff;                                 // the type buffer may have moved
+    sais<int>(s1, SA1, n1, name);
   } else {
     for (int i = 0; i < n1; ++i) SA1[s1[i]] = i;
   }
   // stage 3: induce the result
   get_buckets(cnt, bkt, K, true);
-  for (int i = 1, j = 0; i < n; ++i) if (t[i] && !t[i - 1]) s1[j++] = i;
+  for (int i = 1, j = 0; i < n; ++i) if ((s[i] & 1) && !(s[i - 1] & 1)) s1[j++] = i;
   for (int i = 0; i < n1; ++i) SA1[i] = s1[SA1[i]];
   for (int i = n1; i < n; ++i) SA[i] = -1;
   for (int i = n1 - 1; i >= 0; --i) {
     const int j = SA[i];
     SA[i] = -1;
-    SA[--bkt[s[j]]] = j;
+    SA[--bkt[s[j] >> 1]] = j;
   }
-  induce_l(t, SA, s, cnt, bkt, n, K);
-  induce_s(t, SA, s, cnt, bkt, n, K);
+  induce_l(SA, s, cnt, bkt, n, K);
+  induce_s(SA, s, cnt, bkt, n, K);
 }
 
 // start of the lexicographically least rotation
@@ -243,7 +256,7 @@ void make_code_lengths(unsigned char* len, const int* freq, int alphaSize, int m
 }
 
 struct Scratch {
-  std::vector<unsigned char> block, rot, types;
+  std::vector<unsigned char> block, rot;
   std::vector<int> sa, pi;
   std::vector<unsigned short> mtfv;
 };
@@ -312,7 +325,7 @@ extern "C" int rpcc_bz2_compress(const uint8_t* src, size_t n, uint8_t* dst, siz
       sym.resize((size_t)nb + 1);
       for (int q = 0; q < nb; ++q) sym[q] = (unsigned short)(S.rot[q] + 1);
       sym[nb] = 0;
-      sais<unsigned short>(sym.data(), SA, nb + 1, 257, S.types, 0);
+      sais<unsigned short>(sym.data(), SA, nb + 1, 257);
     }
     TICK(3);
     // SA[0] is the sentinel suffix; ptr[i] = start of the i-th smallest rotation in the original block
