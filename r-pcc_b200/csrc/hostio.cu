@@ -119,34 +119,47 @@ int pack_one(const Bz2* bz, const Job& j, std::vector<unsigned char>& out, std::
     if (tmp.size() < cap) tmp.resize(cap);
     unsigned got = cap;
     const int slot = s + (5 - j.nsec);               // the last four sections line up whether or not salience leads
+    // mode 0: every 256th frame of a worker codes the section with BOTH coders (same input, so the two costs compare
+    // like with like) and keeps the running costs; in between the cheaper one is used
+    bool probe = false;
     int use = mode == 1 ? 1 : 0;                     // 0 = own, 1 = libbz2
     if (mode == 0) {
-      const unsigned k = st.seen[slot]++;
-      if (k == 0) use = 0;
-      else if (k == 1) use = 1;
-      else {
-        use = st.cost[1][slot] < st.cost[0][slot] ? 1 : 0;
-        if ((k & 127u) == 0) use ^= 1;               // the other one gets a turn: the data may have changed
-      }
+      probe = (st.seen[slot]++ & 255u) == 0 && n >= 512;
+      use = st.cost[1][slot] < st.cost[0][slot] ? 1 : 0;
     }
-    const double t0 = now_ns();
     int rc = RPCC_BZ2_DECLINED;
-    if (use == 0) {
+    auto run_own = [&]() -> int {
       size_t got2 = 0;
-      rc = rpcc_bz2_compress(j.sec[s], n, reinterpret_cast<uint8_t*>(tmp.data()), cap, &got2);
+      const int r = rpcc_bz2_compress(j.sec[s], n, reinterpret_cast<uint8_t*>(tmp.data()), cap, &got2);
       got = (unsigned)got2;
-      if (rc != RPCC_OK && rc != RPCC_BZ2_DECLINED) return rc;
-    }
-    if (rc == RPCC_BZ2_DECLINED) {
-      use = 1;
+      return r;
+    };
+    auto run_lib = [&]() -> int {
       got = cap;
-      rc = bz->compress(tmp.data(), &got, reinterpret_cast<char*>(const_cast<unsigned char*>(j.sec[s])), (unsigned)n, 9, 0, j.wf[s]);
-    }
-    if (rc != 0) return RPCC_ERR_ARG;
-    if (n >= 512) {                                  // (tiny sections say nothing about either coder)
+      return bz->compress(tmp.data(), &got, reinterpret_cast<char*>(const_cast<unsigned char*>(j.sec[s])), (unsigned)n, 9, 0, j.wf[s]) == 0 ? RPCC_OK : RPCC_ERR_ARG;
+    };
+    auto note = [&](int which, double t0) {
       const double c = (now_ns() - t0) / (double)n;
-      double& e = st.cost[use][slot];
-      e = e == 0 ? c : 0.75 * e + 0.25 * c;
+      double& e = st.cost[which][slot];
+      e = e == 0 ? c : 0.5 * e + 0.5 * c;
+    };
+    if (probe) {
+      double t0 = now_ns();
+      rc = run_own();
+      if (rc == RPCC_OK) note(0, t0); else if (rc != RPCC_BZ2_DECLINED) return rc;
+      t0 = now_ns();
+      const int r2 = run_lib();                      // (its output is the one kept: identical bytes either way)
+      if (r2 != RPCC_OK) return r2;
+      note(1, t0);
+      if (rc == RPCC_BZ2_DECLINED) st.cost[0][slot] = 1e30;   // the own encoder leaves this kind of section to libbz2
+      rc = RPCC_OK;
+    } else {
+      if (use == 0) {
+        rc = run_own();
+        if (rc != RPCC_OK && rc != RPCC_BZ2_DECLINED) return rc;
+      }
+      if (rc == RPCC_BZ2_DECLINED) rc = run_lib();
+      if (rc != RPCC_OK) return rc;
     }
     const int32_t len32 = (int32_t)got;
     const size_t at = out.size();
