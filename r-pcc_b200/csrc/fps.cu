@@ -379,11 +379,206 @@ constexpr unsigned kNoTie = 0xFFFFFFFFu;
 __device__ __forceinline__ int ford(float f) { const int b = __float_as_int(f); return b ^ ((b >> 31) & 0x7fffffff); }
 __device__ __forceinline__ float ordf(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
 
-template <int THREADS, int Q, int MINB>   // Q buckets per lane: the warp owns buckets warp + NW * (q * 32 + lane)
+// ---- first pass as its own kernel (the default): round 1 over every bucket is plain streaming work -- it wants registers
+//      and many independent warps, the round loop below wants two resident CTAs of 1024 threads at 32 registers.  One warp
+//      takes a run of consecutive buckets of one frame and leaves, per bucket, a 32-byte record {box, max t, tie key} and,
+//      per pixel, t (bit 31 = "masked to the origin") for the round kernel.
+struct __align__(16) FpsBucket { float x0, y0, z0, x1, y1, z1; unsigned bmax, btk; };
+constexpr int kFirstThreads = 256;
+
+// round 1 for the 32 pixels of bucket b (one per lane); every lane returns the same record
+__device__ __forceinline__ FpsBucket fps_first_bucket(const float* __restrict__ rg, const float* __restrict__ lut, int b, int lane,
+                                                      int HW, float g0, float g1, float g2, float g3, float gnorm, float thr,
+                                                      float x1, float y1, float z1, unsigned* __restrict__ temp) {
+  const float INF = __int_as_float(0x7f800000);
+  FpsBucket o = {INF, INF, INF, -INF, -INF, -INF, 0u, kNoTie};
+  const int p = (b << 5) + lane;
+  const bool inb = p < HW;
+  float x = 0.f, y = 0.f, z = 0.f;
+  if (inb) masked_point(ld_stream_f(rg + p), lut + (size_t)p * 3, g0, g1, g2, g3, gnorm, thr, x, y, z);
+  const bool origin = (x == 0.f) && (y == 0.f) && (z == 0.f);
+  const float tv = fminf(fps_dist(x, y, z, x1, y1, z1), 1e10f);
+  if (inb) temp[p] = __float_as_uint(tv) | (origin ? 0x80000000u : 0u);
+  const unsigned nb = inb ? __float_as_uint(tv) : 0u;
+  const unsigned newmax = __reduce_max_sync(0xffffffffu, nb);
+  // A bucket whose running distances are all zero -- ground and empty pixels when seed 0 is one of them, about half
+  // of a frame's buckets -- can never change, and can only be chosen when every point of the frame sits at zero, in
+  // which case the reference's tie rule picks pixel 0 (tie key 0): bucket 0 is always kept, the others keep the
+  // defaults (maximum 0, no tie key, empty box).
+  if (newmax == 0u && b != 0) return o;                     // warp-uniform
+  const unsigned tk = (inb && nb == newmax) ? ((__brev((unsigned)p) & 0xFFC00000u) | ((unsigned)p >> 10)) : kNoTie;
+  o.bmax = newmax;
+  o.btk = __reduce_min_sync(0xffffffffu, tk);
+  // box over the points that can still change (t > 0).  Coordinates inside +-250 m are shifted into (0, 512), where
+  // the bit patterns order like the values (one REDUX each, no order-preserving transform); the shift rounds to
+  // 3e-5 m and the box is widened by 1e-4 m on every side, which keeps the pruning conservative.
+  const bool live = inb && tv > 0.f;
+  if (!__any_sync(0xffffffffu, live && !(fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) < 250.f))) {
+    const unsigned ux = __float_as_uint(x + 256.f), uy = __float_as_uint(y + 256.f), uz = __float_as_uint(z + 256.f);
+    o.x0 = __uint_as_float(__reduce_min_sync(0xffffffffu, live ? ux : 0x7f800000u)) - 256.0001f;
+    o.y0 = __uint_as_float(__reduce_min_sync(0xffffffffu, live ? uy : 0x7f800000u)) - 256.0001f;
+    o.z0 = __uint_as_float(__reduce_min_sync(0xffffffffu, live ? uz : 0x7f800000u)) - 256.0001f;
+    o.x1 = __uint_as_float(__reduce_max_sync(0xffffffffu, live ? ux : 0u)) - 255.9999f;
+    o.y1 = __uint_as_float(__reduce_max_sync(0xffffffffu, live ? uy : 0u)) - 255.9999f;
+    o.z1 = __uint_as_float(__reduce_max_sync(0xffffffffu, live ? uz : 0u)) - 255.9999f;
+  } else {                                                  // coordinates beyond any lidar's range (or NaN): exact order
+    const int big = 0x7fffffff;
+    o.x0 = ordf(__reduce_min_sync(0xffffffffu, live ? ford(x) : big));
+    o.y0 = ordf(__reduce_min_sync(0xffffffffu, live ? ford(y) : big));
+    o.z0 = ordf(__reduce_min_sync(0xffffffffu, live ? ford(z) : big));
+    o.x1 = ordf(__reduce_max_sync(0xffffffffu, live ? ford(x) : -big));
+    o.y1 = ordf(__reduce_max_sync(0xffffffffu, live ? ford(y) : -big));
+    o.z1 = ordf(__reduce_max_sync(0xffffffffu, live ? ford(z) : -big));
+  }
+  return o;
+}
+
+__global__ void __launch_bounds__(kFirstThreads)
+fps_first_pass_kernel(const float* __restrict__ range, const float* __restrict__ lut, const float* __restrict__ ground,
+                      int B, int HW, int NB, int runs, float thr, unsigned* __restrict__ temp_ws, FpsBucket* __restrict__ rec) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (kFirstThreads / 32) + (threadIdx.x >> 5);
+  const int f = w / runs, c = w - f * runs;
+  if (f >= B) return;                                        // warp-uniform
+  const int per = (NB + runs - 1) / runs;
+  const int b0 = c * per, b1 = min(NB, b0 + per);
+  const float* rg = range + (size_t)f * HW;
+  unsigned* temp = temp_ws + (size_t)f * HW;
+  const float g0 = ground[f * 4], g1 = ground[f * 4 + 1], g2 = ground[f * 4 + 2], g3 = ground[f * 4 + 3];
+  const float gnorm = sqrtf(torch_sum3(g0 * g0, g1 * g1, g2 * g2));
+  float x1, y1, z1;                                          // seed 0 is flat index 0 (sampling_gpu.cu:44-46)
+  masked_point(rg[0], lut, g0, g1, g2, g3, gnorm, thr, x1, y1, z1);
+#pragma unroll 2
+  for (int b = b0; b < b1; ++b) {
+    const FpsBucket o = fps_first_bucket(rg, lut, b, lane, HW, g0, g1, g2, g3, gnorm, thr, x1, y1, z1, temp);
+    if (lane == 0) {
+      float4* dst = reinterpret_cast<float4*>(rec + (size_t)f * NB + b);
+      dst[0] = make_float4(o.x0, o.y0, o.z0, o.x1);
+      dst[1] = make_float4(o.y1, o.z1, __uint_as_float(o.bmax), __uint_as_float(o.btk));
+    }
+  }
+}
+
+// The same with four consecutive pixels per lane (H*W a multiple of 4): 128-bit loads and stores, a bucket is 8 lanes, a warp
+// does 4 buckets at a time and the per-bucket reductions are 3-step shuffles.  The ground mask is decided by a * (1/|g|)
+// wherever that is more than 1e-6 (relative) away from the threshold -- the correctly rounded quotient the reference compares
+// is then on the same side -- and by the division itself for the lanes that are not.
+__device__ __forceinline__ float seg8_min(float v) {
+  v = fminf(v, __shfl_xor_sync(0xffffffffu, v, 1)); v = fminf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return fminf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+}
+__device__ __forceinline__ float seg8_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1)); v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+}
+__device__ __forceinline__ unsigned seg8_umin(unsigned v) {
+  v = min(v, __shfl_xor_sync(0xffffffffu, v, 1)); v = min(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return min(v, __shfl_xor_sync(0xffffffffu, v, 4));
+}
+__device__ __forceinline__ unsigned seg8_umax(unsigned v) {
+  v = max(v, __shfl_xor_sync(0xffffffffu, v, 1)); v = max(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return max(v, __shfl_xor_sync(0xffffffffu, v, 4));
+}
+
+__global__ void __launch_bounds__(kFirstThreads)
+fps_first_pass4_kernel(const float* __restrict__ range, const float* __restrict__ lut, const float* __restrict__ ground,
+                       int B, int HW, int NB, int runs, float thr, unsigned* __restrict__ temp_ws, FpsBucket* __restrict__ rec) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (kFirstThreads / 32) + (threadIdx.x >> 5);
+  const int f = w / runs, c = w - f * runs;
+  if (f >= B) return;                                        // warp-uniform
+  const int NG = (HW + 127) >> 7;                            // groups of 4 buckets
+  const int per = (NG + runs - 1) / runs;
+  const int ga = c * per, gb = min(NG, ga + per);
+  const float* rg = range + (size_t)f * HW;
+  uint4* temp4 = reinterpret_cast<uint4*>(temp_ws + (size_t)f * HW);
+  const float4* lut4 = reinterpret_cast<const float4*>(lut);
+  const float g0 = ground[f * 4], g1 = ground[f * 4 + 1], g2 = ground[f * 4 + 2], g3 = ground[f * 4 + 3];
+  const float gnorm = sqrtf(torch_sum3(g0 * g0, g1 * g1, g2 * g2));
+  const float rgn = 1.0f / gnorm, thi = thr + fabsf(thr) * 1e-6f, tlo = thr - fabsf(thr) * 1e-6f;
+  float sx, sy, sz;                                          // seed 0 is flat index 0 (sampling_gpu.cu:44-46)
+  masked_point(rg[0], lut, g0, g1, g2, g3, gnorm, thr, sx, sy, sz);
+  const float INF = __int_as_float(0x7f800000), QNAN = __int_as_float(0x7fc00000);
+  for (int g = ga; g < gb; ++g) {
+    const int p0 = (g << 7) + 4 * lane;
+    const bool inb = p0 < HW;                                // H*W % 4 == 0: all four pixels or none
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f), l0 = r, l1 = r, l2 = r;
+    if (inb) {
+      r = ld_stream_f4(reinterpret_cast<const float4*>(rg + p0));
+      const float4* lp = lut4 + (size_t)(p0 >> 2) * 3;
+      l0 = __ldg(lp); l1 = __ldg(lp + 1); l2 = __ldg(lp + 2);
+    }
+    float x[4] = {r.x * l0.x, r.y * l0.w, r.z * l1.z, r.w * l2.y};
+    float y[4] = {r.x * l0.y, r.y * l1.x, r.z * l1.w, r.w * l2.z};
+    float z[4] = {r.x * l0.z, r.y * l1.y, r.z * l2.x, r.w * l2.w};
+    // ---- ground mask (utils/segment_utils.py:137-139)
+    float a[4];
+    bool keep[4], unsure = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      a[i] = fabsf(torch_sum3(x[i] * g0, y[i] * g1, z[i] * g2) + g3);
+      const float qa = a[i] * rgn;
+      keep[i] = qa > thi;
+      unsure = unsure || !(keep[i] || qa < tlo);
+    }
+    if (__any_sync(0xffffffffu, unsure)) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) keep[i] = a[i] / gnorm > thr;
+    }
+    // ---- round 1: t = min(d(point, seed 0), 1e10)
+    float t[4];
+    unsigned word[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (!keep[i]) { x[i] = 0.f; y[i] = 0.f; z[i] = 0.f; }
+      const bool origin = (x[i] == 0.f) && (y[i] == 0.f) && (z[i] == 0.f);
+      t[i] = fminf(fps_dist(x[i], y[i], z[i], sx, sy, sz), 1e10f);
+      word[i] = __float_as_uint(t[i]) | (origin ? 0x80000000u : 0u);
+    }
+    if (inb) temp4[p0 >> 2] = make_uint4(word[0], word[1], word[2], word[3]);
+    const unsigned t0 = inb ? __float_as_uint(t[0]) : 0u, t1 = inb ? __float_as_uint(t[1]) : 0u;
+    const unsigned t2 = inb ? __float_as_uint(t[2]) : 0u, t3 = inb ? __float_as_uint(t[3]) : 0u;
+    const unsigned bmax = seg8_umax(max(max(t0, t1), max(t2, t3)));
+    const int b = (g << 2) + (lane >> 3);                    // this lane's bucket
+    FpsBucket o = {INF, INF, INF, -INF, -INF, -INF, 0u, kNoTie};
+    // buckets whose running distances are all zero stay at the defaults (see fps_first_bucket); bucket 0 is always kept
+    if (__any_sync(0xffffffffu, bmax != 0u) || g == 0) {
+      // tie key of pixel p0 + i = key(p0) | bitrev(i): the smallest comes first in the order i = 0, 2, 1, 3
+      const unsigned key0 = (__brev((unsigned)p0) & 0xFFC00000u) | ((unsigned)p0 >> 10);
+      unsigned tk = kNoTie;
+      tk = (inb && t3 == bmax) ? (key0 | 0xC0000000u) : tk;
+      tk = (inb && t1 == bmax) ? (key0 | 0x80000000u) : tk;
+      tk = (inb && t2 == bmax) ? (key0 | 0x40000000u) : tk;
+      tk = (inb && t0 == bmax) ? key0 : tk;
+      o.bmax = bmax;
+      o.btk = seg8_umin(tk);
+      // box over the points that can still change (t > 0): the others are NaN, which min / max skip
+      float mn[3] = {QNAN, QNAN, QNAN}, mx[3] = {QNAN, QNAN, QNAN};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool live = inb && t[i] > 0.f;
+        const float lx = live ? x[i] : QNAN, ly = live ? y[i] : QNAN, lz = live ? z[i] : QNAN;
+        mn[0] = fminf(mn[0], lx); mn[1] = fminf(mn[1], ly); mn[2] = fminf(mn[2], lz);
+        mx[0] = fmaxf(mx[0], lx); mx[1] = fmaxf(mx[1], ly); mx[2] = fmaxf(mx[2], lz);
+      }
+      o.x0 = seg8_min(mn[0]); o.y0 = seg8_min(mn[1]); o.z0 = seg8_min(mn[2]);
+      o.x1 = seg8_max(mx[0]); o.y1 = seg8_max(mx[1]); o.z1 = seg8_max(mx[2]);
+      if (!(o.x0 == o.x0)) { o.x0 = INF; o.y0 = INF; o.z0 = INF; o.x1 = -INF; o.y1 = -INF; o.z1 = -INF; }   // no live point
+      if (bmax == 0u && b != 0) o.btk = kNoTie;
+    }
+    if ((lane & 7) == 0 && b < NB) {
+      float4* dst = reinterpret_cast<float4*>(rec + (size_t)f * NB + b);
+      dst[0] = make_float4(o.x0, o.y0, o.z0, o.x1);
+      dst[1] = make_float4(o.y1, o.z1, __uint_as_float(o.bmax), __uint_as_float(o.btk));
+    }
+  }
+}
+
+template <int THREADS, int Q, int MINB, bool SPLIT>   // Q buckets per lane: the warp owns buckets warp + NW * (q * 32 + lane)
 __global__ void __launch_bounds__(THREADS, MINB)
 segment_fps_pruned_kernel(const float* __restrict__ range, const float* __restrict__ lut, const float* __restrict__ ground,
-                          int B, int HW, int m, float thr, unsigned* __restrict__ temp_ws, int* __restrict__ next_frame,
-                          int* __restrict__ center_idx, float* __restrict__ centers) {
+                          int B, int HW, int m, float thr, unsigned* __restrict__ temp_ws, const FpsBucket* __restrict__ rec,
+                          int* __restrict__ next_frame, int* __restrict__ center_idx, float* __restrict__ centers) {
   constexpr int NW = THREADS / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int NB = (HW + 31) >> 5;
@@ -393,7 +588,7 @@ segment_fps_pruned_kernel(const float* __restrict__ range, const float* __restri
   __shared__ uint2 s_part[2][32];
   __shared__ float4 s_win[2];
   __shared__ int s_frame;
-  unsigned* temp = temp_ws + (size_t)blockIdx.x * HW;
+  unsigned* temp = temp_ws + (size_t)blockIdx.x * HW;      // (SPLIT: per frame, set below)
   const float INF = __int_as_float(0x7f800000);
 
   // Frames are handed out by a counter: the number of bucket updates (and so the time) differs by tens of per cent
@@ -415,8 +610,23 @@ segment_fps_pruned_kernel(const float* __restrict__ range, const float* __restri
       float* c = centers + (size_t)f * m * 3;
       c[0] = x1; c[1] = y1; c[2] = z1;
     }
-    // ---- first pass = round 1 over every bucket: t = min(d, 1e10), boxes, maxima, tie keys
+    // ---- round 1 over every bucket: t = min(d, 1e10), boxes, maxima, tie keys
     unsigned bmax[Q], btk[Q];
+    if (SPLIT) {                                              // done by fps_first_pass_kernel: fetch this thread's records
+      temp = temp_ws + (size_t)f * HW;
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const int b = warp + NW * (q * 32 + lane);
+        float4 ra = make_float4(INF, INF, INF, -INF), rb = make_float4(-INF, -INF, 0.f, __uint_as_float(kNoTie));
+        if (b < NB) {
+          const float4* src = reinterpret_cast<const float4*>(rec + (size_t)f * NB + b);
+          ra = ld_stream_f4(src); rb = ld_stream_f4(src + 1);
+        }
+        s_boxa[q * THREADS + tid] = ra;
+        s_boxb[q * THREADS + tid] = make_float2(rb.x, rb.y);
+        bmax[q] = __float_as_uint(rb.z); btk[q] = __float_as_uint(rb.w);
+      }
+    } else {
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
       bmax[q] = 0u; btk[q] = kNoTie;
@@ -468,6 +678,7 @@ segment_fps_pruned_kernel(const float* __restrict__ range, const float* __restri
       // an all-dead / missing bucket keeps (+big, -big): its lower bound is huge and its maximum 0
       s_boxa[q * THREADS + tid] = make_float4(mx0, my0, mz0, mx1);
       s_boxb[q * THREADS + tid] = make_float2(my1, mz1);
+    }
     }
     // (boxes are private to their owner thread: no synchronisation needed before they are read back)
 
@@ -576,10 +787,10 @@ segment_fps_pruned_kernel(const float* __restrict__ range, const float* __restri
   }
 }
 
-template <int THREADS, int Q, int MINB>
+template <int THREADS, int Q, int MINB, bool SPLIT>
 static int launch_fps_pruned(const float* range, const float* lut, const float* ground, int B, int HW, int m, float thr,
                              int* center_idx, float* centers, cudaStream_t st) {
-  auto kern = segment_fps_pruned_kernel<THREADS, Q, MINB>;
+  auto kern = segment_fps_pruned_kernel<THREADS, Q, MINB, SPLIT>;
   const size_t smem = sizeof(float) * 6 * Q * THREADS;
   RPCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
@@ -587,16 +798,34 @@ static int launch_fps_pruned(const float* range, const float* lut, const float* 
   if (per_sm < 1) per_sm = 1;
   int grid = per_sm * sm_count();
   if (grid > B) grid = B;
-  // running distances of the frames in flight: stream-ordered scratch, no synchronisation
+  const int NB = (HW + 31) >> 5;
+  // running distances (SPLIT: of every frame, else of the frames in flight) and the buckets' records: stream-ordered
+  // scratch, no synchronisation
   void* ws = nullptr;
   cudaMemPool_t pool = nullptr;
   { const int rc = scratch_pool(&pool); if (rc != RPCC_OK) return rc; }
-  const size_t ws_bytes = sizeof(unsigned) * (size_t)grid * HW;
-  RPCC_CUDA(cudaMallocFromPoolAsync(&ws, ws_bytes + 256, pool, st));
-  int* counter = reinterpret_cast<int*>(static_cast<unsigned char*>(ws) + ws_bytes);   // frame queue head
+  const size_t temp_bytes = sizeof(unsigned) * (size_t)(SPLIT ? B : grid) * HW;
+  const size_t rec_bytes = SPLIT ? sizeof(FpsBucket) * (size_t)B * NB : 0;
+  const size_t rec_off = (temp_bytes + 255) & ~(size_t)255;
+  const size_t ctr_off = rec_off + ((rec_bytes + 255) & ~(size_t)255);
+  RPCC_CUDA(cudaMallocFromPoolAsync(&ws, ctr_off + 256, pool, st));
+  unsigned char* base = static_cast<unsigned char*>(ws);
+  FpsBucket* rec = reinterpret_cast<FpsBucket*>(base + rec_off);
+  int* counter = reinterpret_cast<int*>(base + ctr_off);     // frame queue head
   cudaError_t le = cudaMemsetAsync(counter, 0, sizeof(int), st);
+  if (le == cudaSuccess && SPLIT) {
+    const int runs = 32;                                     // warps per frame: ~125 buckets each at 64 x 2000
+    const long long warps = (long long)B * runs;
+    const int wpb = kFirstThreads / 32;
+    const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
+    const bool vec4 = HW % 4 == 0 && (reinterpret_cast<uintptr_t>(range) | reinterpret_cast<uintptr_t>(lut)) % 16 == 0;
+    if (vec4) fps_first_pass4_kernel<<<blocks, kFirstThreads, 0, st>>>(range, lut, ground, B, HW, NB, runs, thr, static_cast<unsigned*>(ws), rec);
+    else fps_first_pass_kernel<<<blocks, kFirstThreads, 0, st>>>(range, lut, ground, B, HW, NB, runs, thr, static_cast<unsigned*>(ws), rec);
+    le = cudaGetLastError();
+    count_launch();
+  }
   if (le == cudaSuccess) {
-    kern<<<grid, THREADS, smem, st>>>(range, lut, ground, B, HW, m, thr, static_cast<unsigned*>(ws), counter, center_idx, centers);
+    kern<<<grid, THREADS, smem, st>>>(range, lut, ground, B, HW, m, thr, static_cast<unsigned*>(ws), rec, counter, center_idx, centers);
     le = cudaGetLastError();
   }
   RPCC_CUDA(cudaFreeAsync(ws, st));
@@ -634,7 +863,9 @@ extern "C" int rpcc_segment_fps_batch(const float* range, const float* lut, cons
     cudaStream_t st = as_stream(stream);
     const int NB = (HW + 31) / 32;
     static const int minb = getenv("RPCC_FPS_MINB") ? atoi(getenv("RPCC_FPS_MINB")) : 2;
-#define RPCC_FPS_GO(T, Q, M) return launch_fps_pruned<T, Q, M>(range, lut, ground, B, HW, m, ground_thr, center_idx, centers, st)
+    static const bool split = !(getenv("RPCC_FPS_SPLIT") && atoi(getenv("RPCC_FPS_SPLIT")) == 0);
+#define RPCC_FPS_GO(T, Q, M) return split ? launch_fps_pruned<T, Q, M, true>(range, lut, ground, B, HW, m, ground_thr, center_idx, centers, st) \
+                                          : launch_fps_pruned<T, Q, M, false>(range, lut, ground, B, HW, m, ground_thr, center_idx, centers, st)
     if (fps_threads == 512) {
       const int q = (NB + 511) / 512;
       if (q <= 2) RPCC_FPS_GO(512, 2, 2);
