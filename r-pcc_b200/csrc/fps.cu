@@ -787,6 +787,267 @@ segment_fps_pruned_kernel(const float* __restrict__ range, const float* __restri
   }
 }
 
+static cudaError_t launch_first_pass(const float* range, const float* lut, const float* ground, int B, int HW, int NB, float thr,
+                                     unsigned* temp_ws, FpsBucket* rec, cudaStream_t st) {
+  const int runs = 32;                                       // warps per frame: ~125 buckets each at 64 x 2000
+  const long long warps = (long long)B * runs;
+  const int wpb = kFirstThreads / 32;
+  const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
+  const bool vec4 = HW % 4 == 0 && (reinterpret_cast<uintptr_t>(range) | reinterpret_cast<uintptr_t>(lut)) % 16 == 0;
+  if (vec4) fps_first_pass4_kernel<<<blocks, kFirstThreads, 0, st>>>(range, lut, ground, B, HW, NB, runs, thr, temp_ws, rec);
+  else fps_first_pass_kernel<<<blocks, kFirstThreads, 0, st>>>(range, lut, ground, B, HW, NB, runs, thr, temp_ws, rec);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---- the rounds with two buckets per step.  More than half of the instructions of the kernel above, and the longest
+//      dependent chain of a round, are the bucket updates: a warp walks its touched buckets one at a time, five loads and
+//      one trip to L2 each.  Here a bucket is 16 lanes x 2 consecutive pixels (64-bit loads), so a warp updates TWO of its
+//      touched buckets per step -- half the load instructions, half the address arithmetic, half the round trips -- and
+//      the two new maxima come from one REDUX each.  The tie key of a bucket is no longer kept: a round's winner is
+//      found by scanning the one bucket that holds the frame's maximum (the load warp 0 made anyway to fetch the
+//      centre's coordinates, 32 lanes wide now); only when several buckets hold the very same maximum -- the origin
+//      points when seed 0 is not one of them, or equal distances -- do all warps scan their candidates (TIE below).
+//      Needs H*W even and 8-byte aligned images (every lidar of the reference); the kernel above remains for the rest.
+__device__ __forceinline__ unsigned fps_tie_key(unsigned p) { return (__brev(p) & 0xFFC00000u) | (p >> 10); }
+
+template <int Q>
+__global__ void __launch_bounds__(1024, 2)
+segment_fps_pair_kernel(const float* __restrict__ range, const float* __restrict__ lut, const float* __restrict__ ground,
+                        int B, int HW, int m, float thr, unsigned* __restrict__ temp_ws, const FpsBucket* __restrict__ rec,
+                        int* __restrict__ next_frame, int* __restrict__ center_idx, float* __restrict__ centers) {
+  constexpr int THREADS = 1024, NW = 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NB = (HW + 31) >> 5;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* s_boxa = reinterpret_cast<float4*>(smem_raw);          // [Q][THREADS]: x0, y0, z0, x1 of bucket (q, tid)
+  float2* s_boxb = reinterpret_cast<float2*>(s_boxa + Q * THREADS);   // [Q][THREADS]: y1, z1
+  __shared__ uint2 s_part[2][32];
+  __shared__ float4 s_win[2];
+  __shared__ int s_frame;
+  const float INF = __int_as_float(0x7f800000);
+  const bool hi = lane >= 16;                                // which bucket of a step this lane works on
+  const int sub = (lane & 15) << 1;                          // its first pixel inside the bucket
+
+  for (;;) {
+    if (tid == 0) s_frame = atomicAdd(next_frame, 1);
+    __syncthreads();
+    const int f = s_frame;
+    if (f >= B) break;
+    const float* rg = range + (size_t)f * HW;
+    unsigned* temp = temp_ws + (size_t)f * HW;
+    float sx, sy, sz;                                          // seed 0 is flat index 0 (sampling_gpu.cu:44-46)
+    {
+      const float g0 = ground[f * 4], g1 = ground[f * 4 + 1], g2 = ground[f * 4 + 2], g3 = ground[f * 4 + 3];
+      masked_point(rg[0], lut, g0, g1, g2, g3, sqrtf(torch_sum3(g0 * g0, g1 * g1, g2 * g2)), thr, sx, sy, sz);
+    }
+    const bool seed0_origin = (sx == 0.f) && (sy == 0.f) && (sz == 0.f);
+    if (tid == 0) {
+      center_idx[(size_t)f * m] = 0;
+      float* c = centers + (size_t)f * m * 3;
+      c[0] = sx; c[1] = sy; c[2] = sz;
+    }
+    // ---- round 1 was done by the first-pass kernel: boxes to shared memory, maxima to registers
+    unsigned bmax[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int b = warp + NW * (q * 32 + lane);
+      float4 ra = make_float4(INF, INF, INF, -INF), rb = make_float4(-INF, -INF, 0.f, 0.f);
+      if (b < NB) {
+        const float4* src = reinterpret_cast<const float4*>(rec + (size_t)f * NB + b);
+        ra = ld_stream_f4(src); rb = ld_stream_f4(src + 1);
+      }
+      s_boxa[q * THREADS + tid] = ra;
+      s_boxb[q * THREADS + tid] = make_float2(rb.x, rb.y);
+      bmax[q] = __float_as_uint(rb.z);
+    }
+    float x1 = sx, y1 = sy, z1 = sz;
+
+    for (int j = 1; j < m; ++j) {
+      // ---- winner of the previous round: the largest bucket maximum, then the point inside that bucket
+      {
+        unsigned d = bmax[0];
+        int bq = 0, same = 1;                                  // how many of this lane's buckets hold d
+#pragma unroll
+        for (int q = 1; q < Q; ++q) {
+          same = bmax[q] > d ? 1 : same + (bmax[q] == d ? 1 : 0);
+          bq = bmax[q] > d ? q : bq;
+          d = max(d, bmax[q]);
+        }
+        const unsigned dw = __reduce_max_sync(0xffffffffu, d);
+        const unsigned holders = __reduce_add_sync(0xffffffffu, d == dw ? (unsigned)same : 0u);
+        const unsigned code = __reduce_min_sync(0xffffffffu, d == dw ? (unsigned)(bq * 32 + lane) : 0xFFFFu);
+        if (lane == 0) s_part[j & 1][warp] = make_uint2(dw, (unsigned)(warp + NW * (int)code) | (holders > 1u ? 0x80000000u : 0u));
+        __syncthreads();
+        if (warp == 0) {
+          const uint2 v = s_part[j & 1][lane];
+          const unsigned dmax = __reduce_max_sync(0xffffffffu, v.x);
+          const unsigned cand = __ballot_sync(0xffffffffu, v.x == dmax);
+          const bool several = (cand & (cand - 1u)) != 0u || __any_sync(0xffffffffu, v.x == dmax && (v.y >> 31) != 0u);
+          if (dmax == 0u) {
+            // every running distance is zero: the tie rule picks pixel 0, which is seed 0 again
+            if (lane == 0) {
+              s_win[j & 1] = make_float4(sx, sy, sz, 0.f);
+              center_idx[(size_t)f * m + j] = 0;
+              float* c = centers + ((size_t)f * m + j) * 3;
+              c[0] = sx; c[1] = sy; c[2] = sz;
+            }
+          } else if (!several) {
+            const int bstar = (int)(__shfl_sync(0xffffffffu, v.y, __ffs(cand) - 1) & 0x7fffffffu);
+            const int p = (bstar << 5) + lane;
+            const bool inb = p < HW;
+            unsigned tb = 0u;
+            float r = 0.f, wx = 0.f, wy = 0.f, wz = 0.f;
+            if (inb) {
+              tb = temp[p];
+              r = ld_stream_f(rg + p);
+              wx = ld_stream_f(lut + (size_t)p * 3); wy = ld_stream_f(lut + (size_t)p * 3 + 1); wz = ld_stream_f(lut + (size_t)p * 3 + 2);
+            }
+            const unsigned tk = (inb && (tb & 0x7fffffffu) == dmax) ? fps_tie_key((unsigned)p) : kNoTie;
+            const unsigned tkmin = __reduce_min_sync(0xffffffffu, tk);
+            if (tk == tkmin) {                                 // tie keys are unique: one lane (the bucket holds dmax)
+              const bool org = (tb >> 31) != 0u;
+              const float cx = org ? 0.f : r * wx, cy = org ? 0.f : r * wy, cz = org ? 0.f : r * wz;
+              s_win[j & 1] = make_float4(cx, cy, cz, 0.f);
+              center_idx[(size_t)f * m + j] = p;
+              float* c = centers + ((size_t)f * m + j) * 3;
+              c[0] = cx; c[1] = cy; c[2] = cz;
+            }
+          } else if (lane == 0) {
+            s_win[j & 1] = make_float4(__uint_as_float(dmax), 0.f, 0.f, 1.f);    // TIE: resolved by all warps below
+          }
+        }
+        __syncthreads();
+        float4 w = s_win[j & 1];
+        if (w.w != 0.f) {                                      // block-uniform
+          // TIE: every warp scans its buckets that hold the maximum for the smallest tie key
+          const unsigned dmax = __float_as_uint(w.x);
+          unsigned tkw = kNoTie;
+#pragma unroll
+          for (int q = 0; q < Q; ++q) {
+            unsigned cm = __ballot_sync(0xffffffffu, bmax[q] == dmax);
+            while (cm) {
+              const int t = __ffs(cm) - 1;
+              cm &= cm - 1;
+              const int p = ((warp + NW * (q * 32 + t)) << 5) + lane;
+              const bool hit = p < HW && (temp[p] & 0x7fffffffu) == dmax;
+              tkw = min(tkw, __reduce_min_sync(0xffffffffu, hit ? fps_tie_key((unsigned)p) : kNoTie));
+            }
+          }
+          if (lane == 0) s_part[j & 1][warp] = make_uint2(tkw, 0u);      // (warp 0 read the maxima before the last barrier)
+          __syncthreads();
+          if (warp == 0) {
+            const unsigned tkmin = __reduce_min_sync(0xffffffffu, s_part[j & 1][lane].x);
+            if (lane == 0) {
+              const int k = (int)(((tkmin & 0x3FFFFFu) << 10) | __brev(tkmin & 0xFFC00000u));
+              const float r = ld_stream_f(rg + k);
+              const float wx = ld_stream_f(lut + (size_t)k * 3), wy = ld_stream_f(lut + (size_t)k * 3 + 1), wz = ld_stream_f(lut + (size_t)k * 3 + 2);
+              const bool org = (temp[k] >> 31) != 0u;
+              const float cx = org ? 0.f : r * wx, cy = org ? 0.f : r * wy, cz = org ? 0.f : r * wz;
+              s_win[j & 1] = make_float4(cx, cy, cz, 0.f);
+              center_idx[(size_t)f * m + j] = k;
+              float* c = centers + ((size_t)f * m + j) * 3;
+              c[0] = cx; c[1] = cy; c[2] = cz;
+            }
+          }
+          __syncthreads();
+          w = s_win[j & 1];
+        }
+        x1 = w.x; y1 = w.y; z1 = w.z;
+      }
+      if (j == m - 1) break;                                  // the last centre needs no update pass
+      // ---- per q: which of my buckets can change, then update them two at a time with the reference arithmetic.  When
+      //      seed 0 is an origin point (a ground or empty pixel 0: the usual case) every origin point sits at t = 0 for
+      //      good -- min(d, 0) = 0 whatever coordinates go in -- so the masked points need not be re-zeroed.
+      auto update = [&](auto simple) {
+  #pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          unsigned act;
+          {
+            const float4 ba = s_boxa[q * THREADS + tid];
+            const float2 bb = s_boxb[q * THREADS + tid];
+            const float ox = fmaxf(fmaxf(ba.x - x1, x1 - ba.w), 0.f);
+            const float oy = fmaxf(fmaxf(ba.y - y1, y1 - bb.x), 0.f);
+            const float oz = fmaxf(fmaxf(ba.z - z1, z1 - bb.y), 0.f);
+            const float lb = __fmaf_rn(oz, oz, __fmaf_rn(oy, oy, ox * ox));
+            act = __ballot_sync(0xffffffffu, lb * 0.99999f < __uint_as_float(bmax[q]));
+          }
+          while (act) {                                          // warp-uniform
+            const int ta = __ffs(act) - 1;
+            act &= act - 1;
+            int tb_ = 32;                                        // no second bucket: the upper half idles
+            if (act) { tb_ = __ffs(act) - 1; act &= act - 1; }
+            const int tm = hi ? tb_ : ta;
+            const int p = ((warp + NW * (q * 32 + tm)) << 5) + sub;
+            unsigned nb = 0u;
+            if (tm < 32 && p < HW) {                             // H*W is even: both pixels or none
+              const uint2 told = *reinterpret_cast<const uint2*>(temp + p);
+              const float2 r = __ldg(reinterpret_cast<const float2*>(rg + p));
+              const float2* l2 = reinterpret_cast<const float2*>(lut + (size_t)p * 3);
+              const float2 la = __ldg(l2), lb2 = __ldg(l2 + 1), lc = __ldg(l2 + 2);
+              float xa = r.x * la.x, ya = r.x * la.y, za = r.x * lb2.x;
+              float xb = r.y * lb2.y, yb = r.y * lc.x, zb = r.y * lc.y;
+              if (!decltype(simple)::value) {
+                const bool oa = (told.x >> 31) != 0u, ob = (told.y >> 31) != 0u;
+                xa = oa ? 0.f : xa; ya = oa ? 0.f : ya; za = oa ? 0.f : za;
+                xb = ob ? 0.f : xb; yb = ob ? 0.f : yb; zb = ob ? 0.f : zb;
+              }
+              const float oa_ = __uint_as_float(told.x & 0x7fffffffu), ob_ = __uint_as_float(told.y & 0x7fffffffu);
+              const float na = fminf(fps_dist(xa, ya, za, x1, y1, z1), oa_);          // sampling_gpu.cu:64-66
+              const float nb_ = fminf(fps_dist(xb, yb, zb, x1, y1, z1), ob_);
+              if (na != oa_ || nb_ != ob_)
+                *reinterpret_cast<uint2*>(temp + p) = make_uint2(__float_as_uint(na) | (told.x & 0x80000000u),
+                                                                 __float_as_uint(nb_) | (told.y & 0x80000000u));
+              nb = max(__float_as_uint(na), __float_as_uint(nb_));
+            }
+            const unsigned ma = __reduce_max_sync(0xffffffffu, hi ? 0u : nb);
+            const unsigned mb = __reduce_max_sync(0xffffffffu, hi ? nb : 0u);
+            bmax[q] = lane == ta ? ma : bmax[q];
+            bmax[q] = lane == tb_ ? mb : bmax[q];
+          }
+        }
+      };
+      if (seed0_origin) update(std::true_type()); else update(std::false_type());
+    }
+    __syncthreads();   // the next frame rewrites the boxes, s_part and s_frame
+  }
+}
+
+template <int Q>
+static int launch_fps_pair(const float* range, const float* lut, const float* ground, int B, int HW, int m, float thr,
+                           int* center_idx, float* centers, cudaStream_t st) {
+  auto kern = segment_fps_pair_kernel<Q>;
+  const size_t smem = sizeof(float) * 6 * Q * 1024;
+  RPCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  RPCC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 1024, smem));
+  if (per_sm < 1) per_sm = 1;
+  int grid = per_sm * sm_count();
+  if (grid > B) grid = B;
+  const int NB = (HW + 31) >> 5;
+  void* ws = nullptr;                                        // running distances + bucket records + frame queue head
+  cudaMemPool_t pool = nullptr;
+  { const int rc = scratch_pool(&pool); if (rc != RPCC_OK) return rc; }
+  const size_t temp_bytes = sizeof(unsigned) * (size_t)B * HW;
+  const size_t rec_bytes = sizeof(FpsBucket) * (size_t)B * NB;
+  const size_t rec_off = (temp_bytes + 255) & ~(size_t)255;
+  const size_t ctr_off = rec_off + ((rec_bytes + 255) & ~(size_t)255);
+  RPCC_CUDA(cudaMallocFromPoolAsync(&ws, ctr_off + 256, pool, st));
+  unsigned char* base = static_cast<unsigned char*>(ws);
+  FpsBucket* rec = reinterpret_cast<FpsBucket*>(base + rec_off);
+  int* counter = reinterpret_cast<int*>(base + ctr_off);
+  cudaError_t le = cudaMemsetAsync(counter, 0, sizeof(int), st);
+  if (le == cudaSuccess) le = launch_first_pass(range, lut, ground, B, HW, NB, thr, static_cast<unsigned*>(ws), rec, st);
+  if (le == cudaSuccess) {
+    kern<<<grid, 1024, smem, st>>>(range, lut, ground, B, HW, m, thr, static_cast<unsigned*>(ws), rec, counter, center_idx, centers);
+    le = cudaGetLastError();
+  }
+  RPCC_CUDA(cudaFreeAsync(ws, st));
+  RPCC_CUDA(le);
+  count_launch();
+  return RPCC_OK;
+}
+
 template <int THREADS, int Q, int MINB, bool SPLIT>
 static int launch_fps_pruned(const float* range, const float* lut, const float* ground, int B, int HW, int m, float thr,
                              int* center_idx, float* centers, cudaStream_t st) {
@@ -813,17 +1074,7 @@ static int launch_fps_pruned(const float* range, const float* lut, const float* 
   FpsBucket* rec = reinterpret_cast<FpsBucket*>(base + rec_off);
   int* counter = reinterpret_cast<int*>(base + ctr_off);     // frame queue head
   cudaError_t le = cudaMemsetAsync(counter, 0, sizeof(int), st);
-  if (le == cudaSuccess && SPLIT) {
-    const int runs = 32;                                     // warps per frame: ~125 buckets each at 64 x 2000
-    const long long warps = (long long)B * runs;
-    const int wpb = kFirstThreads / 32;
-    const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
-    const bool vec4 = HW % 4 == 0 && (reinterpret_cast<uintptr_t>(range) | reinterpret_cast<uintptr_t>(lut)) % 16 == 0;
-    if (vec4) fps_first_pass4_kernel<<<blocks, kFirstThreads, 0, st>>>(range, lut, ground, B, HW, NB, runs, thr, static_cast<unsigned*>(ws), rec);
-    else fps_first_pass_kernel<<<blocks, kFirstThreads, 0, st>>>(range, lut, ground, B, HW, NB, runs, thr, static_cast<unsigned*>(ws), rec);
-    le = cudaGetLastError();
-    count_launch();
-  }
+  if (le == cudaSuccess && SPLIT) le = launch_first_pass(range, lut, ground, B, HW, NB, thr, static_cast<unsigned*>(ws), rec, st);
   if (le == cudaSuccess) {
     kern<<<grid, THREADS, smem, st>>>(range, lut, ground, B, HW, m, thr, static_cast<unsigned*>(ws), rec, counter, center_idx, centers);
     le = cudaGetLastError();
@@ -863,6 +1114,13 @@ extern "C" int rpcc_segment_fps_batch(const float* range, const float* lut, cons
     cudaStream_t st = as_stream(stream);
     const int NB = (HW + 31) / 32;
     static const int minb = getenv("RPCC_FPS_MINB") ? atoi(getenv("RPCC_FPS_MINB")) : 2;
+    static const bool pair = !(getenv("RPCC_FPS_PAIR") && atoi(getenv("RPCC_FPS_PAIR")) == 0);
+    if (pair && NB <= 4096 && HW % 2 == 0 && (reinterpret_cast<uintptr_t>(range) | reinterpret_cast<uintptr_t>(lut)) % 8 == 0) {
+      const int q = (NB + 1023) / 1024;
+      if (q <= 1) return launch_fps_pair<1>(range, lut, ground, B, HW, m, ground_thr, center_idx, centers, st);
+      if (q <= 2) return launch_fps_pair<2>(range, lut, ground, B, HW, m, ground_thr, center_idx, centers, st);
+      return launch_fps_pair<4>(range, lut, ground, B, HW, m, ground_thr, center_idx, centers, st);
+    }
     static const bool split = !(getenv("RPCC_FPS_SPLIT") && atoi(getenv("RPCC_FPS_SPLIT")) == 0);
 #define RPCC_FPS_GO(T, Q, M) return split ? launch_fps_pruned<T, Q, M, true>(range, lut, ground, B, HW, m, ground_thr, center_idx, centers, st) \
                                           : launch_fps_pruned<T, Q, M, false>(range, lut, ground, B, HW, m, ground_thr, center_idx, centers, st)

@@ -117,21 +117,22 @@ __device__ __forceinline__ void quantize_tile(const float* __restrict__ rg, cons
     // ---- table look-ups; the ray directions of the pixels whose row is a plane are requested now (L2) and used after
     //      the rank / contour work of the step, which needs neither them nor the prediction
     float pred[kQSlices], inv[kQSlices];
-    unsigned plane = 0;                          // bit j: slice j's row is a plane
+    bool plane[kQSlices], some_plane = false;    // slice j's row is a plane: its 1 / step is stored negated
 #pragma unroll
     for (int j = 0; j < kQSlices; ++j) {
       const float4 tb = lds_f4(tab_addr + (unsigned)lab[j] * 16u);
       pred[j] = tb.x;
       inv[j] = tb.z;
-      plane |= tb.w != 0.0f ? (1u << j) : 0u;
+      plane[j] = tb.z < 0.0f;
+      some_plane = some_plane || plane[j];
     }
-    const bool any_plane = __any_sync(0xffffffffu, plane != 0u);   // the ground row is a plane, in every frame
+    const bool any_plane = __any_sync(0xffffffffu, some_plane);   // the ground row is a plane, in every frame
     float lx[kQSlices], ly[kQSlices], lz[kQSlices];
     if (any_plane) {
 #pragma unroll
       for (int j = 0; j < kQSlices; ++j) {
         lx[j] = 0.f; ly[j] = 0.f; lz[j] = 0.f;
-        if (plane & (1u << j)) {
+        if (plane[j]) {
           const float* t3 = lut + (size_t)(p_step + j * 32 + (int)lane) * 3;
           lx[j] = __ldg(t3); ly[j] = __ldg(t3 + 1); lz[j] = __ldg(t3 + 2);
         }
@@ -158,13 +159,13 @@ __device__ __forceinline__ void quantize_tile(const float* __restrict__ rg, cons
       const unsigned cb = __ballot_sync(0xffffffffu, c);
       if (c) stg_elem(sq, nseq + __popc(cb & lt), l);
       nseq += __popc(cb);
-      if ((int)lane == s * kQSlices + j) myword = __byte_perm(__brev(cb), 0, 0x0123);   // np.packbits: pixel p0+i -> byte i/8, bit 7-(i%8)
+      if ((int)lane == s * kQSlices + j) myword = cb;
     }
     // ---- symbols (cpp_modules.cpp:264-281, tools/compress.py:106, cpp_modules.cpp:311-331)
     if (any_plane) {
 #pragma unroll
       for (int j = 0; j < kQSlices; ++j) {
-        if (plane & (1u << j)) {
+        if (plane[j]) {
           const float4 m = lds_f4(model_addr + (unsigned)lab[j] * 16u);
           pred[j] = -m.w / (m.x * lx[j] + m.y * ly[j] + m.z * lz[j]);   // cpp_modules.cpp:273-279
         }
@@ -178,7 +179,7 @@ __device__ __forceinline__ void quantize_tile(const float* __restrict__ rg, cons
     bool near = false;
 #pragma unroll
     for (int j = 0; j < kQSlices; ++j) {
-      const float t = (r[j] - pred[j]) * inv[j];
+      const float t = (r[j] - pred[j]) * fabsf(inv[j]);
       q[j] = __float2int_rn(t);
       near = near || !(__fmaf_rn(fabsf(t), 1e-6f, fabsf(t - (float)q[j])) < 0.5f);
     }
@@ -186,7 +187,7 @@ __device__ __forceinline__ void quantize_tile(const float* __restrict__ rg, cons
 #pragma unroll
       for (int j = 0; j < kQSlices; ++j) {
         const float res = r[j] - pred[j];
-        const float t = res * inv[j];
+        const float t = res * fabsf(inv[j]);
         if (!(__fmaf_rn(fabsf(t), 1e-6f, fabsf(t - (float)q[j])) < 0.5f))
           q[j] = (int)roundf(res / lds_f4(tab_addr + (unsigned)lab[j] * 16u).y);
       }
@@ -197,6 +198,7 @@ __device__ __forceinline__ void quantize_tile(const float* __restrict__ rg, cons
   }
   // ---- contour bytes of the tile: lane i holds the word of slice i (np.packbits bytes 4i .. 4i+3 of the tile)
   {
+    myword = __byte_perm(__brev(myword), 0, 0x0123);   // np.packbits: pixel p0+i -> byte i/8, bit 7-(i%8)
     const int byte0 = (p_tile >> 3) + 4 * (int)lane;
     if ((cbytes & 3) == 0 && byte0 + 4 <= cbytes) {
       *reinterpret_cast<unsigned*>(cbits + byte0) = myword;
@@ -217,7 +219,7 @@ quantize_pack_kernel(const float* __restrict__ range, const uint8_t* __restrict_
                      const unsigned long long* __restrict__ sym_base, const unsigned long long* __restrict__ seq_base) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* s_model = reinterpret_cast<float4*>(smem_raw);            // [K]
-  float4* s_tab = s_model + K;                                      // [K] constant prediction, step, 1 / step, plane flag
+  float4* s_tab = s_model + K;                                      // [K] constant prediction, step, 1 / step (negated: the row is a plane), -
   unsigned* s_cnt = reinterpret_cast<unsigned*>(s_tab + K);         // [kQWarps][K] next symbol position per label
 
   const int f = blockIdx.y, tid = threadIdx.x;
@@ -227,7 +229,7 @@ quantize_pack_kernel(const float* __restrict__ range, const uint8_t* __restrict_
     const float4 m = reinterpret_cast<const float4*>(model)[(size_t)f * K + l];
     s_model[l] = m;
     const float st = step_per_label ? step_per_label[(size_t)f * K + l] : step;
-    s_tab[l] = make_float4(m.w, st, 1.0f / st, (m.x + m.y + m.z == 0) ? 0.0f : 1.0f);
+    s_tab[l] = make_float4(m.w, st, (m.x + m.y + m.z == 0) ? 1.0f / st : -(1.0f / st), 0.0f);
   }
   unsigned* cnt = s_cnt + warp * K;
   if (tile < T)
@@ -313,7 +315,7 @@ quantize_pack_staged_kernel(const float* __restrict__ range, const uint8_t* __re
   const unsigned long long qbase = seq_base ? __ldg(seq_base + f) : (unsigned long long)f * seq_stride;
   if (tid < K) {
     s_model[tid] = m;
-    s_tab[tid] = make_float4(m.w, st, 1.0f / st, (m.x + m.y + m.z == 0) ? 0.0f : 1.0f);
+    s_tab[tid] = make_float4(m.w, st, (m.x + m.y + m.z == 0) ? 1.0f / st : -(1.0f / st), 0.0f);
   }
   unsigned* cnt = s_cnt + warp * K;
 #pragma unroll

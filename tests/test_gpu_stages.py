@@ -256,6 +256,34 @@ def test_segment_fps_when_seed_zero_is_a_real_point(T, R):
         assert np.array_equal(labels[b].cpu().numpy().astype(np.int64), seg_t), b
 
 
+@pytest.mark.parametrize("lidar", LIDARS)
+def test_segment_fps_with_exact_ties_between_buckets(T, R, lidar):
+    """The round kernel keeps one maximum per 32-pixel bucket and finds a round's winner inside the single bucket that holds
+    the frame's maximum; when several buckets hold the very same value every warp scans its candidates for the smallest
+    tie key.  Range images that force that path: a sphere (every ray the same length: symmetric distances all over the
+    image), ranges rounded to whole metres, and an empty frame; ground far away (nothing masked) and a real one."""
+    import refimpl
+    pts, off, grounds = _frames(R, lidar, [3])
+    cfg, rng = _project_dev(T, R, pts, off, lidar)
+    lut = cfg.transform_map()
+    real = rng[0].cpu().numpy()
+    H, W = real.shape
+    images = [np.full((H, W), 10.0, np.float32), np.round(real), np.zeros((H, W), np.float32)]
+    half = np.full((H, W), 7.0, np.float32)
+    half[:, W // 2:] = 0.0                                 # half of the image empty
+    images.append(half)
+    ri = np.stack(images).astype(np.float32)
+    for g4 in ([0.0, 0.0, 1.0, 100.0], list(grounds[0])):
+        g = np.tile(np.array([g4], np.float32), (len(images), 1))
+        d_r, d_lut, d_g = T.from_numpy(ri).cuda(), T.from_numpy(lut).cuda(), T.from_numpy(g).cuda()
+        cidx, centers = R.device_mod.segment_fps_batch(d_r, d_lut, d_g, 100, 0.1)
+        T.cuda.synchronize()
+        for b in range(len(images)):
+            _, cidx_t, ng_t = refimpl.torch_segment(ri[b], lut, g[b], 100)
+            assert np.array_equal(cidx[b].cpu().numpy(), cidx_t), (lidar, b, g4)
+            assert np.array_equal(centers[b].cpu().numpy(), ng_t[cidx_t]), (lidar, b, g4)
+
+
 def test_segment_example_frame(T, R, example_points):
     import refimpl
     off = np.array([0, example_points.shape[0]], np.int64)
