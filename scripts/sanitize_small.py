@@ -24,5 +24,12 @@ for lidar, nonuniform, method in cases:
     xyz = d["xyz"][0].reshape(-1, 3).cpu().numpy()
     r = calc_chamfer_distance(pts[off[0]:off[1], :3][::8], xyz[::8], out=False)
     print(lidar, nonuniform, method, [len(b) for b in blobs], "chamfer mean %.4f" % r["mean"])
+# the FPS round kernel's tie path (several buckets hold the frame's maximum): a sphere, nothing masked
+from rpcc_b200 import LidarConfig, device  # noqa: E402
+cfg = LidarConfig("VelodyneVLP16")
+lut = torch.from_numpy(cfg.transform_map()).cuda()
+sphere = torch.full((2, cfg.H, cfg.W), 10.0, device="cuda")
+cidx, _ = device.segment_fps_batch(sphere, lut, torch.tensor([[0.0, 0.0, 1.0, 100.0]] * 2, device="cuda"), 100, 0.1)
+print("tie path seeds", cidx[0, :6].tolist())
 torch.cuda.synchronize()
 print("done")

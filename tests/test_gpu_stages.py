@@ -284,6 +284,29 @@ def test_segment_fps_with_exact_ties_between_buckets(T, R, lidar):
             assert np.array_equal(centers[b].cpu().numpy(), ng_t[cidx_t]), (lidar, b, g4)
 
 
+def test_segment_fps_odd_image_takes_the_generic_kernels(T, R):
+    """An image with an odd number of pixels (no lidar of the reference has one) cannot use the 64-bit / 128-bit paths:
+    the one-bucket-per-step round kernel and the scalar first pass take over.  Seeds and labels against the oracle."""
+    g = np.random.default_rng(5)
+    H, W = 11, 101                                           # 1111 pixels
+    az = np.linspace(0, 2 * np.pi, W, endpoint=False)[None, :]
+    el = np.linspace(-0.4, 0.1, H)[:, None]
+    lut = np.stack([np.cos(el) * np.cos(az), np.cos(el) * np.sin(az), np.sin(el) * np.ones_like(az)], -1).astype(np.float32)
+    ri = (5.0 + 20.0 * g.random((3, H, W))).astype(np.float32)
+    ri[g.random((3, H, W)) < 0.1] = 0.0
+    ri[1, 0, 0] = 0.0                                        # seed 0 an origin point in one frame, a real point in another
+    ri[2, 0, 0] = 9.0
+    ground = np.tile(np.array([[0.0, 0.0, 1.0, 1.7]], np.float32), (3, 1))
+    d_r, d_lut, d_g = T.from_numpy(ri).cuda(), T.from_numpy(lut).cuda(), T.from_numpy(ground).cuda()
+    cidx, centers = R.device_mod.segment_fps_batch(d_r, d_lut, d_g, 40, 0.1)
+    labels, _ = R.device_mod.assign_labels_batch(d_r, d_lut, d_g, centers)
+    T.cuda.synchronize()
+    for b in range(3):
+        seg_o, cidx_o, _ = oracle.segment(ri[b], lut, ground[b], 40)
+        assert np.array_equal(cidx[b].cpu().numpy(), cidx_o), b
+        assert np.array_equal(labels[b].cpu().numpy().astype(np.int64), seg_o), b
+
+
 def test_segment_example_frame(T, R, example_points):
     import refimpl
     off = np.array([0, example_points.shape[0]], np.int64)
