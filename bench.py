@@ -611,6 +611,29 @@ def main():
                                "what": "rpcc_b200.tools.compress_datalist over %d KITTI .bin files (hard links to 32 distinct "
                                        "frames, page-cache warm) sharded over %d rank(s): file reads -> GPU chain -> bzip2 on "
                                        "the native pool -> .rpcc files; bound by libbz2 on the host cores" % (a.datalist_frames, world)}
+            # full-size consistency (outside the timed region): the corpus is `distinct` frames under many names, and a
+            # file's bytes may depend on nothing but its points -- every copy of a frame, on whichever rank and in whichever
+            # batch it landed, must have produced the same .rpcc
+            import hashlib
+            import json as _json
+            digests = {}
+            for i in range(lo, hi):
+                with open(compress_datalist.output_path_for(os.path.join(root, "out"), names[i]), "rb") as fh:
+                    digests.setdefault(i % 32, set()).add(hashlib.sha256(fh.read()).hexdigest())
+            with open(os.path.join(root, "digests_%d.json" % rank), "w") as fh:
+                _json.dump({str(k): sorted(v) for k, v in digests.items()}, fh)
+            barrier()
+            if rank == 0:
+                merged = {}
+                for r in range(world):
+                    for k, v in _json.load(open(os.path.join(root, "digests_%d.json" % r))).items():
+                        merged.setdefault(k, set()).update(v)
+                bad = sorted(k for k, v in merged.items() if len(v) != 1)
+                e2e["datalist"]["consistency"] = {"files_hashed": a.datalist_frames, "distinct_frames": len(merged),
+                                                  "distinct_outputs": sum(len(v) for v in merged.values()),
+                                                  "ok": not bad}
+                if bad:
+                    raise SystemExit("bench: copies of frames %s produced different .rpcc bytes" % bad[:8])
             barrier()
             if local == 0:
                 shutil.rmtree(root, ignore_errors=True)

@@ -164,7 +164,12 @@ assign_labels_kernel(const float* __restrict__ range, const float* __restrict__ 
       // max(best) + R of the sphere centre: slices of ground pixels (residuals of centimetres) keep no centre at all
       const float reach = fminf(sqrt_approx(dmin) * 1.00001f + 2.0f * R, (maxb * 1.00001f + R) * 1.00001f);
       const float thr2 = reach * reach * 1.00001f;
+      // Survivors are evaluated in ascending centre index with a strict '<' (torch.max's first-index rule).  The square
+      // root is taken only when some lane can still improve: sqrtf is correctly rounded and monotone, so a squared
+      // distance s >= RU(best * best) gives sqrtf(s) >= best and cannot win.  (NaN / inf on either side fail the
+      // comparison below and take the square root, as before.)
       int bi = 0;
+      float best2 = __fmul_ru(best, best);
 #pragma unroll
       for (int q = 0; q < MQ; ++q) {
         unsigned surv = __ballot_sync(0xffffffffu, d2[q] * 0.99999f <= thr2);
@@ -174,8 +179,11 @@ assign_labels_kernel(const float* __restrict__ range, const float* __restrict__ 
           const int ci = q * 32 + b;
           const float4 cc = s_c[ci];
           const float dx = x - cc.x, dy = y - cc.y, dz = z - cc.z;
-          const float v = sqrtf(torch_sum3(dx * dx, dy * dy, dz * dz));   // channel ci + 1 (:144, :25-26)
-          if (v < best) { best = v; bi = ci + 1; }
+          const float s2 = torch_sum3(dx * dx, dy * dy, dz * dz);
+          if (__any_sync(0xffffffffu, valid && !(s2 >= best2))) {
+            const float v = sqrtf(s2);                                     // channel ci + 1 (:144, :25-26)
+            if (v < best) { best = v; bi = ci + 1; best2 = __fmul_ru(v, v); }
+          }
         }
       }
       if (valid) label = bi > 0 ? bi + 1 : 0;          // :168-169

@@ -21,7 +21,13 @@
 
 namespace rpcc {
 
-constexpr int kQWarps = 8;                  // one 1024-pixel tile per warp, 8 tiles per CTA
+#ifndef RPCC_QWARPS
+#define RPCC_QWARPS 8
+#endif
+#ifndef RPCC_QSOCC
+#define RPCC_QSOCC 4
+#endif
+constexpr int kQWarps = RPCC_QWARPS;        // one 1024-pixel tile per warp, 8 tiles per CTA
 constexpr int kQThreads = kQWarps * 32;
 #ifndef RPCC_QSLICES
 #define RPCC_QSLICES 2
@@ -163,6 +169,8 @@ __device__ __forceinline__ void quantize_tile(const float* __restrict__ rg, cons
     }
     // ---- symbols (cpp_modules.cpp:264-281, tools/compress.py:106, cpp_modules.cpp:311-331)
     if (any_plane) {
+      // (a branch-free form -- every lane divides, constant predictions as pred / 1 -- measured 0.456 ms against 0.385:
+      //  the slices without a plane row skip the division here)
 #pragma unroll
       for (int j = 0; j < kQSlices; ++j) {
         if (plane[j]) {
@@ -263,7 +271,7 @@ constexpr int kQsLabPad = 16;                                         // bytes i
 constexpr int kQsWarpBytes = RPCC_TILE * 4 + kQsLabPad + RPCC_TILE;   // 5136
 
 template <typename SymT, bool CLAMP, bool WIDE>
-__global__ void __launch_bounds__(kQThreads, 4)
+__global__ void __launch_bounds__(kQThreads, RPCC_QSOCC)
 quantize_pack_staged_kernel(const float* __restrict__ range, const uint8_t* __restrict__ labels, const float* __restrict__ model,
                             const float* __restrict__ lut, Book bk, const float* __restrict__ step_per_label, float step,
                             int HW, int W, int K, int T, SymT* __restrict__ symbols, size_t sym_stride,
@@ -305,17 +313,28 @@ quantize_pack_staged_kernel(const float* __restrict__ range, const uint8_t* __re
   }
   unsigned coff = 0;
   if (live) coff = __ldg(bk.tile_coff + (size_t)f * T + tile);
-  float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
-  float st = step;
-  if (tid < K) {                                                   // K <= 254 < kQThreads
-    m = __ldg(reinterpret_cast<const float4*>(model) + (size_t)f * K + tid);
-    if (step_per_label) st = __ldg(step_per_label + (size_t)f * K + tid);
+  constexpr int kRows = (254 + kQThreads - 1) / kQThreads;          // model rows per thread (K <= 254)
+  float4 m[kRows];
+  float st[kRows];
+#pragma unroll
+  for (int i = 0; i < kRows; ++i) {
+    const int l = tid + i * kQThreads;
+    m[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    st[i] = step;
+    if (l < K) {
+      m[i] = __ldg(reinterpret_cast<const float4*>(model) + (size_t)f * K + l);
+      if (step_per_label) st[i] = __ldg(step_per_label + (size_t)f * K + l);
+    }
   }
   const unsigned long long sbase = sym_base ? __ldg(sym_base + f) : (unsigned long long)f * sym_stride;
   const unsigned long long qbase = seq_base ? __ldg(seq_base + f) : (unsigned long long)f * seq_stride;
-  if (tid < K) {
-    s_model[tid] = m;
-    s_tab[tid] = make_float4(m.w, st, (m.x + m.y + m.z == 0) ? 1.0f / st : -(1.0f / st), 0.0f);
+#pragma unroll
+  for (int i = 0; i < kRows; ++i) {
+    const int l = tid + i * kQThreads;
+    if (l < K) {
+      s_model[l] = m[i];
+      s_tab[l] = make_float4(m[i].w, st[i], (m[i].x + m[i].y + m[i].z == 0) ? 1.0f / st[i] : -(1.0f / st[i]), 0.0f);
+    }
   }
   unsigned* cnt = s_cnt + warp * K;
 #pragma unroll
