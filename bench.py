@@ -62,6 +62,7 @@ def parse():
                     help="frames per upload/kernels/download pipeline stage of encode_host (0 = one per SM)")
     ap.add_argument("--datalist-frames", type=int, default=8192, help="files of the config-5 run, all ranks together (0 = skip)")
     ap.add_argument("--datalist-batch", type=int, default=592)
+    ap.add_argument("--no-numa-bind", action="store_true", help="leave the process on whatever CPUs the launcher gave it")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -413,6 +414,11 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
+    # one process per GPU: stay on the CPUs (and so the memory) next to it; undone before the cpu_baseline leg, which is
+    # entitled to every host core
+    from rpcc_b200.shard import bind_to_gpu_numa
+    all_cpus = os.sched_getaffinity(0)
+    numa_cpus = None if a.no_numa_bind else bind_to_gpu_numa(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -556,7 +562,8 @@ def main():
                "link_ceiling_frames_per_s_all_gpus": float(sum(all_ranks(link_ceiling))),
                "note": "bound by the upload of the points over PCIe: link_ceiling = what the ranks' links, probed at the same "
                        "moment with plain copies, could carry",
-               "kitti_rows_16B": kitti_rows}
+               "kitti_rows_16B": kitti_rows,
+               "cpus_per_rank_after_numa_binding": all_ranks(float(len(numa_cpus)) if numa_cpus else 0.0)}
 
         # ---- e2e.decode: .rpcc streams (host bytes) -> rows of the output .bin files in pinned host memory
         ND = min(EF, 592)
@@ -688,12 +695,13 @@ def main():
                         "the latency/issue-bound FPS and label kernels, see kernels{}", "kernels": kernels}
 
     cpu_baseline = None
+    os.sched_setaffinity(0, all_cpus)
     if not a.no_cpu_baseline:
         import oracle  # noqa: F401  (checker; the one CPU leg of this arm)
         from oracle import ref
         use_ref = ref.have_cpp()
         cores = os.cpu_count() or 1
-        n = a.cpu_frames or max(2 * cores, 16)
+        n = a.cpu_frames or max(10 * cores, 64)        # ~0.1 s of CPU per frame: 10-30 s of CPU work, ~1 s of wall clock
         fps, dt, split = cpu_throughput(n, cores, use_ref)
         cpu_baseline = {"value": fps, "unit": UNIT, "cores": cores, "kind": "reference C++ + port(segment)" if use_ref else "port",
                         "sample": "%d frames of the same synthetic 64E workload in %.1f s on %d host processes (%s for the CPU "

@@ -28,7 +28,7 @@ import torch.distributed as dist
 from ..batch import BatchEncoder, eval_summary
 from ..compress_utils import BasicCompressor, pack_bitstream
 from ..hostio import read_bin_xyz
-from ..shard import gather_metrics, shard_range
+from ..shard import bind_to_gpu_numa, gather_metrics, shard_range
 from .common import base_parser, resolve
 
 # columns of the per-frame metrics table that the ranks all-gather
@@ -109,6 +109,8 @@ def compress(args, rank=None, world=None, collective=True):
     rank = int(os.environ.get("RANK", "0")) if rank is None else int(rank)
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:       # a rank of a torchrun job: stay next to its GPU
+        bind_to_gpu_numa(local)
     if collective and world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))

@@ -14,7 +14,7 @@ import time
 import torch
 
 from ..batch import BatchDecoder
-from ..shard import shard_range
+from ..shard import bind_to_gpu_numa, shard_range
 from .common import base_parser, resolve
 
 
@@ -35,6 +35,8 @@ def decompress(args, rank=None, world=None):
     rank = int(os.environ.get("RANK", "0")) if rank is None else int(rank)
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:       # a rank of a torchrun job: stay next to its GPU
+        bind_to_gpu_numa(local)
     files = [l.strip() for l in open(args.datalist) if l.strip()]
     for f in files:
         assert f.split(".")[-1] == "rpcc", f           # decompress_datalist.py:96

@@ -287,3 +287,14 @@ def test_packer_coders_agree(tmp_path, monkeypatch, coder):
     pk.close()
     for b in range(B):
         assert blobs[b, :sizes[b]].tobytes() == oracle.write_rpcc(secs[b]), (coder, b)
+
+
+def test_cpulist_parsing_and_numa_binding_is_harmless_without_topology(tmp_path):
+    """shard.bind_to_gpu_numa: the kernel's cpulist format, and no effect (and no exception) where the GPU's sysfs node
+    is missing -- this container has neither a GPU nor a NUMA topology."""
+    from rpcc_b200.shard import bind_to_gpu_numa, parse_cpulist
+    assert parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa(0, sysfs=str(tmp_path)) is None
+    assert os.sched_getaffinity(0) == before
