@@ -82,21 +82,24 @@ __device__ __forceinline__ void quantize_tile(const float* __restrict__ rg, cons
                                               uint8_t* __restrict__ cbits, int cbytes, int p_tile, int HW, int W, int K,
                                               unsigned lane) {
   const unsigned lt = lanemask_lt();
-  // the one pixel of this tile that starts an image row (cpp_modules.cpp:537), or -1
-  int row_px = -1;
+  // the one pixel of this tile that starts an image row (cpp_modules.cpp:537): slice row_sl, lane row_ln -- or none.
+  // Every per-slice test below compares against the slice counter, the only induction variable besides the two
+  // shared-memory cursors.
+  int row_sl = -1;
   if (WIDE) {
-    const int nr = ((p_tile + W - 1) / W) * W;
-    row_px = nr < p_tile + RPCC_TILE ? nr : -1;
+    const int nr = ((p_tile + W - 1) / W) * W - p_tile;      // offset of the next row start inside the tile
+    if (nr < RPCC_TILE && (nr & 31) == (int)lane) row_sl = nr >> 5;
   }
   const float* rp = rg + p_tile + (int)lane;     // this lane's pixel of the current slice
   const uint8_t* lp = lb + p_tile + (int)lane;
+  unsigned rcur = rng_addr + 4u * lane, lcur = lab_addr + lane;   // STAGED: the same in shared memory
   unsigned nseq = 0;                             // idx_sequence entries emitted by this tile so far
   unsigned myword = 0;                           // contour word of slice `lane` of the tile
   asm volatile("" : "+l"(sym), "+l"(sq));        // keep the two stream bases in one register pair each
 
 #pragma unroll kQUnroll
-  for (int s = 0; s < kQSteps; ++s) {
-    const int p_step = p_tile + s * (32 * kQSlices);
+  for (int k = 0; k < RPCC_TILE / 32; k += kQSlices) {       // k: first slice of the step
+    const int p_step = p_tile + k * 32;
     if (!FULL && p_step >= HW) break;
     float r[kQSlices];
     int lab[kQSlices], lft[kQSlices];
@@ -105,10 +108,9 @@ __device__ __forceinline__ void quantize_tile(const float* __restrict__ rg, cons
       const int p = p_step + j * 32 + (int)lane;
       const bool inb = FULL || p < HW;
       if (STAGED) {
-        const unsigned o = (unsigned)(s * (32 * kQSlices) + j * 32) + lane;
-        r[j] = inb ? lds_f32(rng_addr + 4u * o) : 0.f;
-        lab[j] = inb ? (int)lds_u8(lab_addr + o) : 1;
-        lft[j] = (int)lds_u8(lab_addr + o - 1u);
+        r[j] = inb ? lds_f32(rcur + 128u * j) : 0.f;
+        lab[j] = inb ? (int)lds_u8(lcur + 32u * j) : 1;
+        lft[j] = (int)lds_u8(lcur + 32u * j - 1u);
       } else {
         r[j] = inb ? ld_stream_f(rp + j * 32) : 0.f;
         lab[j] = inb ? (int)__ldg(lp + j * 32) : 1;
@@ -120,16 +122,18 @@ __device__ __forceinline__ void quantize_tile(const float* __restrict__ rg, cons
     }
     rp += 32 * kQSlices;
     lp += 32 * kQSlices;
+    rcur += 128u * kQSlices;
+    lcur += 32u * kQSlices;
     // ---- table look-ups; the ray directions of the pixels whose row is a plane are requested now (L2) and used after
     //      the rank / contour work of the step, which needs neither them nor the prediction
     float pred[kQSlices], inv[kQSlices];
     bool plane[kQSlices], some_plane = false;    // slice j's row is a plane: its 1 / step is stored negated
 #pragma unroll
     for (int j = 0; j < kQSlices; ++j) {
-      const float4 tb = lds_f4(tab_addr + (unsigned)lab[j] * 16u);
+      const float2 tb = lds_f2(tab_addr + (unsigned)lab[j] * 16u);
       pred[j] = tb.x;
-      inv[j] = tb.z;
-      plane[j] = tb.z < 0.0f;
+      inv[j] = tb.y;
+      plane[j] = tb.y < 0.0f;
       some_plane = some_plane || plane[j];
     }
     const bool any_plane = __any_sync(0xffffffffu, some_plane);   // the ground row is a plane, in every frame
@@ -160,17 +164,18 @@ __device__ __forceinline__ void quantize_tile(const float* __restrict__ rg, cons
       __syncwarp();
       pos[j] = base + __popc(grp & lt);
       // contour bit (cpp_modules.cpp:534-545) and idx_sequence
-      const bool rowstart = WIDE ? (p == row_px) : (p % W) == 0;
+      const bool rowstart = WIDE ? (row_sl == k + j) : (p % W) == 0;
       const bool c = inb && (rowstart || l != lft[j]);
       const unsigned cb = __ballot_sync(0xffffffffu, c);
       if (c) stg_elem(sq, nseq + __popc(cb & lt), l);
       nseq += __popc(cb);
-      if ((int)lane == s * kQSlices + j) myword = cb;
+      if ((int)lane == k + j) myword = cb;
     }
     // ---- symbols (cpp_modules.cpp:264-281, tools/compress.py:106, cpp_modules.cpp:311-331)
     if (any_plane) {
-      // (a branch-free form -- every lane divides, constant predictions as pred / 1 -- measured 0.456 ms against 0.385:
-      //  the slices without a plane row skip the division here)
+      // (measured and not kept: a branch-free form in which every lane divides, 0.456 ms against 0.385; the plane
+      //  prediction by a reciprocal product with an exact fallback for the lanes near a rounding boundary, 0.381 ms --
+      //  one per cent for an error analysis that would have to hold for every model a caller can pass)
 #pragma unroll
       for (int j = 0; j < kQSlices; ++j) {
         if (plane[j]) {
@@ -197,7 +202,7 @@ __device__ __forceinline__ void quantize_tile(const float* __restrict__ rg, cons
         const float res = r[j] - pred[j];
         const float t = res * fabsf(inv[j]);
         if (!(__fmaf_rn(fabsf(t), 1e-6f, fabsf(t - (float)q[j])) < 0.5f))
-          q[j] = (int)roundf(res / lds_f4(tab_addr + (unsigned)lab[j] * 16u).y);
+          q[j] = (int)roundf(res / lds_f32(tab_addr + (unsigned)lab[j] * 16u + 8u));
       }
     }
 #pragma unroll
@@ -227,7 +232,7 @@ quantize_pack_kernel(const float* __restrict__ range, const uint8_t* __restrict_
                      const unsigned long long* __restrict__ sym_base, const unsigned long long* __restrict__ seq_base) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* s_model = reinterpret_cast<float4*>(smem_raw);            // [K]
-  float4* s_tab = s_model + K;                                      // [K] constant prediction, step, 1 / step (negated: the row is a plane), -
+  float4* s_tab = s_model + K;                                      // [K] constant prediction, 1 / step (negated: the row is a plane), step, -
   unsigned* s_cnt = reinterpret_cast<unsigned*>(s_tab + K);         // [kQWarps][K] next symbol position per label
 
   const int f = blockIdx.y, tid = threadIdx.x;
@@ -237,7 +242,7 @@ quantize_pack_kernel(const float* __restrict__ range, const uint8_t* __restrict_
     const float4 m = reinterpret_cast<const float4*>(model)[(size_t)f * K + l];
     s_model[l] = m;
     const float st = step_per_label ? step_per_label[(size_t)f * K + l] : step;
-    s_tab[l] = make_float4(m.w, st, (m.x + m.y + m.z == 0) ? 1.0f / st : -(1.0f / st), 0.0f);
+    s_tab[l] = make_float4(m.w, (m.x + m.y + m.z == 0) ? 1.0f / st : -(1.0f / st), st, 0.0f);
   }
   unsigned* cnt = s_cnt + warp * K;
   if (tile < T)
@@ -333,7 +338,7 @@ quantize_pack_staged_kernel(const float* __restrict__ range, const uint8_t* __re
     const int l = tid + i * kQThreads;
     if (l < K) {
       s_model[l] = m[i];
-      s_tab[l] = make_float4(m[i].w, st[i], (m[i].x + m[i].y + m[i].z == 0) ? 1.0f / st[i] : -(1.0f / st[i]), 0.0f);
+      s_tab[l] = make_float4(m[i].w, (m[i].x + m[i].y + m[i].z == 0) ? 1.0f / st[i] : -(1.0f / st[i]), st[i], 0.0f);
     }
   }
   unsigned* cnt = s_cnt + warp * K;
