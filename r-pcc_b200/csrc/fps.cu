@@ -800,25 +800,31 @@ static cudaError_t launch_first_pass(const float* range, const float* lut, const
   return cudaGetLastError();
 }
 
-// ---- the rounds with two buckets per step.  More than half of the instructions of the kernel above, and the longest
-//      dependent chain of a round, are the bucket updates: a warp walks its touched buckets one at a time, five loads and
-//      one trip to L2 each.  Here a bucket is 16 lanes x 2 consecutive pixels (64-bit loads), so a warp updates TWO of its
-//      touched buckets per step -- half the load instructions, half the address arithmetic, half the round trips -- and
-//      the two new maxima come from one REDUX each.  The tie key of a bucket is no longer kept: a round's winner is
-//      found by scanning the one bucket that holds the frame's maximum (the load warp 0 made anyway to fetch the
-//      centre's coordinates, 32 lanes wide now); only when several buckets hold the very same maximum -- the origin
-//      points when seed 0 is not one of them, or equal distances -- do all warps scan their candidates (TIE below).
-//      Needs H*W even and 8-byte aligned images (every lidar of the reference); the kernel above remains for the rest.
 __device__ __forceinline__ unsigned fps_tie_key(unsigned p) { return (__brev(p) & 0xFFC00000u) | (p >> 10); }
 
-template <int Q>
-__global__ void __launch_bounds__(1024, 2)
-segment_fps_pair_kernel(const float* __restrict__ range, const float* __restrict__ lut, const float* __restrict__ ground,
+// ---- the rounds with 64-pixel buckets (the default).  More than half of the instructions of the kernel above, and the
+//      longest dependent chain of a round, are the bucket updates: a warp walks its touched buckets one at a time, five
+//      32-bit loads and one trip to L2 each.  Here a bucket is one warp wide at two consecutive pixels per lane (64-bit
+//      loads): half as many boxes to keep (48 KB per frame at 64 x 2000) and to test, half as many update steps.  The
+//      box of a bucket is the union of the two 32-pixel boxes the first pass leaves, its maximum the larger of the two.
+//      The tie key of a bucket is no longer kept: a round's winner is found by scanning the one bucket that holds the
+//      frame's maximum (the load warp 0 made anyway to fetch the centre's coordinates, 32 lanes wide now); only when
+//      several buckets hold the very same maximum -- the origin points when seed 0 is not one of them, or equal
+//      distances -- do all warps scan their candidates (TIE below).  Needs H*W even and 8-byte aligned images (every
+//      lidar of the reference); the kernel above remains for the rest.
+//      Measured on 1184 frames of 64 x 2000 (profiles/r02h_fps_pair_ab.txt, r02j_fps_wide_ab.txt): one 32-pixel bucket
+//      per step 2.70 ms, two per step (16 lanes x 2 pixels each) 2.43-2.47 ms, 64-pixel buckets 2.26 ms at two CTAs of
+//      1024 threads per SM -- and 2.51 ms at FOUR CTAs of 512 threads (a third fewer instructions, 46 % issue
+//      utilisation): what shortens a round is warps working on the same frame, not more frames per SM.
+template <int THREADS, int Q, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+segment_fps_wide_kernel(const float* __restrict__ range, const float* __restrict__ lut, const float* __restrict__ ground,
                         int B, int HW, int m, float thr, unsigned* __restrict__ temp_ws, const FpsBucket* __restrict__ rec,
                         int* __restrict__ next_frame, int* __restrict__ center_idx, float* __restrict__ centers) {
-  constexpr int THREADS = 1024, NW = 32;
+  constexpr int NW = THREADS / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int NB = (HW + 31) >> 5;
+  const int NB = (HW + 31) >> 5;                             // the first pass's 32-pixel buckets
+  const int NB2 = (HW + 63) >> 6;                            // this kernel's
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* s_boxa = reinterpret_cast<float4*>(smem_raw);          // [Q][THREADS]: x0, y0, z0, x1 of bucket (q, tid)
   float2* s_boxb = reinterpret_cast<float2*>(s_boxa + Q * THREADS);   // [Q][THREADS]: y1, z1
@@ -826,8 +832,6 @@ segment_fps_pair_kernel(const float* __restrict__ range, const float* __restrict
   __shared__ float4 s_win[2];
   __shared__ int s_frame;
   const float INF = __int_as_float(0x7f800000);
-  const bool hi = lane >= 16;                                // which bucket of a step this lane works on
-  const int sub = (lane & 15) << 1;                          // its first pixel inside the bucket
 
   for (;;) {
     if (tid == 0) s_frame = atomicAdd(next_frame, 1);
@@ -847,15 +851,20 @@ segment_fps_pair_kernel(const float* __restrict__ range, const float* __restrict
       float* c = centers + (size_t)f * m * 3;
       c[0] = sx; c[1] = sy; c[2] = sz;
     }
-    // ---- round 1 was done by the first-pass kernel: boxes to shared memory, maxima to registers
+    // ---- round 1 was done by the first-pass kernel: two of its records make a bucket
     unsigned bmax[Q];
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
       const int b = warp + NW * (q * 32 + lane);
       float4 ra = make_float4(INF, INF, INF, -INF), rb = make_float4(-INF, -INF, 0.f, 0.f);
-      if (b < NB) {
-        const float4* src = reinterpret_cast<const float4*>(rec + (size_t)f * NB + b);
+      if (b < NB2) {
+        const float4* src = reinterpret_cast<const float4*>(rec + (size_t)f * NB + 2 * b);
         ra = ld_stream_f4(src); rb = ld_stream_f4(src + 1);
+        if (2 * b + 1 < NB) {
+          const float4 sa = ld_stream_f4(src + 2), sb = ld_stream_f4(src + 3);
+          ra = make_float4(fminf(ra.x, sa.x), fminf(ra.y, sa.y), fminf(ra.z, sa.z), fmaxf(ra.w, sa.w));
+          rb = make_float4(fmaxf(rb.x, sb.x), fmaxf(rb.y, sb.y), __uint_as_float(max(__float_as_uint(rb.z), __float_as_uint(sb.z))), 0.f);
+        }
       }
       s_boxa[q * THREADS + tid] = ra;
       s_boxb[q * THREADS + tid] = make_float2(rb.x, rb.y);
@@ -880,9 +889,9 @@ segment_fps_pair_kernel(const float* __restrict__ range, const float* __restrict
         if (lane == 0) s_part[j & 1][warp] = make_uint2(dw, (unsigned)(warp + NW * (int)code) | (holders > 1u ? 0x80000000u : 0u));
         __syncthreads();
         if (warp == 0) {
-          const uint2 v = s_part[j & 1][lane];
+          const uint2 v = lane < NW ? s_part[j & 1][lane] : make_uint2(0u, 0u);
           const unsigned dmax = __reduce_max_sync(0xffffffffu, v.x);
-          const unsigned cand = __ballot_sync(0xffffffffu, v.x == dmax);
+          const unsigned cand = __ballot_sync(0xffffffffu, lane < NW && v.x == dmax);
           const bool several = (cand & (cand - 1u)) != 0u || __any_sync(0xffffffffu, v.x == dmax && (v.y >> 31) != 0u);
           if (dmax == 0u) {
             // every running distance is zero: the tie rule picks pixel 0, which is seed 0 again
@@ -894,22 +903,27 @@ segment_fps_pair_kernel(const float* __restrict__ range, const float* __restrict
             }
           } else if (!several) {
             const int bstar = (int)(__shfl_sync(0xffffffffu, v.y, __ffs(cand) - 1) & 0x7fffffffu);
-            const int p = (bstar << 5) + lane;
-            const bool inb = p < HW;
-            unsigned tb = 0u;
-            float r = 0.f, wx = 0.f, wy = 0.f, wz = 0.f;
-            if (inb) {
-              tb = temp[p];
-              r = ld_stream_f(rg + p);
-              wx = ld_stream_f(lut + (size_t)p * 3); wy = ld_stream_f(lut + (size_t)p * 3 + 1); wz = ld_stream_f(lut + (size_t)p * 3 + 2);
+            const int p = (bstar << 6) + (lane << 1);
+            uint2 tb = make_uint2(0u, 0u);
+            float2 r = make_float2(0.f, 0.f), la = r, lb2 = r, lc = r;
+            if (p < HW) {                                      // H*W is even: both pixels or none
+              tb = *reinterpret_cast<const uint2*>(temp + p);
+              r = __ldg(reinterpret_cast<const float2*>(rg + p));
+              const float2* l2 = reinterpret_cast<const float2*>(lut + (size_t)p * 3);
+              la = __ldg(l2); lb2 = __ldg(l2 + 1); lc = __ldg(l2 + 2);
             }
-            const unsigned tk = (inb && (tb & 0x7fffffffu) == dmax) ? fps_tie_key((unsigned)p) : kNoTie;
+            const unsigned ka = (p < HW && (tb.x & 0x7fffffffu) == dmax) ? fps_tie_key((unsigned)p) : kNoTie;
+            const unsigned kb = (p < HW && (tb.y & 0x7fffffffu) == dmax) ? fps_tie_key((unsigned)p + 1u) : kNoTie;
+            const unsigned tk = min(ka, kb);
             const unsigned tkmin = __reduce_min_sync(0xffffffffu, tk);
             if (tk == tkmin) {                                 // tie keys are unique: one lane (the bucket holds dmax)
-              const bool org = (tb >> 31) != 0u;
-              const float cx = org ? 0.f : r * wx, cy = org ? 0.f : r * wy, cz = org ? 0.f : r * wz;
+              const bool second = kb < ka;
+              const bool org = ((second ? tb.y : tb.x) >> 31) != 0u;
+              const float rr = second ? r.y : r.x;
+              const float wx = second ? lb2.y : la.x, wy = second ? lc.x : la.y, wz = second ? lc.y : lb2.x;
+              const float cx = org ? 0.f : rr * wx, cy = org ? 0.f : rr * wy, cz = org ? 0.f : rr * wz;
               s_win[j & 1] = make_float4(cx, cy, cz, 0.f);
-              center_idx[(size_t)f * m + j] = p;
+              center_idx[(size_t)f * m + j] = p + (second ? 1 : 0);
               float* c = centers + ((size_t)f * m + j) * 3;
               c[0] = cx; c[1] = cy; c[2] = cz;
             }
@@ -929,15 +943,20 @@ segment_fps_pair_kernel(const float* __restrict__ range, const float* __restrict
             while (cm) {
               const int t = __ffs(cm) - 1;
               cm &= cm - 1;
-              const int p = ((warp + NW * (q * 32 + t)) << 5) + lane;
-              const bool hit = p < HW && (temp[p] & 0x7fffffffu) == dmax;
-              tkw = min(tkw, __reduce_min_sync(0xffffffffu, hit ? fps_tie_key((unsigned)p) : kNoTie));
+              const int p = ((warp + NW * (q * 32 + t)) << 6) + (lane << 1);
+              unsigned tk = kNoTie;
+              if (p < HW) {
+                const uint2 tb = *reinterpret_cast<const uint2*>(temp + p);
+                if ((tb.x & 0x7fffffffu) == dmax) tk = fps_tie_key((unsigned)p);
+                if ((tb.y & 0x7fffffffu) == dmax) tk = min(tk, fps_tie_key((unsigned)p + 1u));
+              }
+              tkw = min(tkw, __reduce_min_sync(0xffffffffu, tk));
             }
           }
           if (lane == 0) s_part[j & 1][warp] = make_uint2(tkw, 0u);      // (warp 0 read the maxima before the last barrier)
           __syncthreads();
           if (warp == 0) {
-            const unsigned tkmin = __reduce_min_sync(0xffffffffu, s_part[j & 1][lane].x);
+            const unsigned tkmin = __reduce_min_sync(0xffffffffu, lane < NW ? s_part[j & 1][lane].x : kNoTie);
             if (lane == 0) {
               const int k = (int)(((tkmin & 0x3FFFFFu) << 10) | __brev(tkmin & 0xFFC00000u));
               const float r = ld_stream_f(rg + k);
@@ -956,11 +975,11 @@ segment_fps_pair_kernel(const float* __restrict__ range, const float* __restrict
         x1 = w.x; y1 = w.y; z1 = w.z;
       }
       if (j == m - 1) break;                                  // the last centre needs no update pass
-      // ---- per q: which of my buckets can change, then update them two at a time with the reference arithmetic.  When
-      //      seed 0 is an origin point (a ground or empty pixel 0: the usual case) every origin point sits at t = 0 for
-      //      good -- min(d, 0) = 0 whatever coordinates go in -- so the masked points need not be re-zeroed.
+      // ---- per q: which of my buckets can change, then update them with the reference arithmetic.  When seed 0 is an
+      //      origin point (a ground or empty pixel 0: the usual case) every origin point sits at t = 0 for good --
+      //      min(d, 0) = 0 whatever coordinates go in -- so the masked points need not be re-zeroed.
       auto update = [&](auto simple) {
-  #pragma unroll
+#pragma unroll
         for (int q = 0; q < Q; ++q) {
           unsigned act;
           {
@@ -972,15 +991,12 @@ segment_fps_pair_kernel(const float* __restrict__ range, const float* __restrict
             const float lb = __fmaf_rn(oz, oz, __fmaf_rn(oy, oy, ox * ox));
             act = __ballot_sync(0xffffffffu, lb * 0.99999f < __uint_as_float(bmax[q]));
           }
-          while (act) {                                          // warp-uniform
-            const int ta = __ffs(act) - 1;
+          while (act) {                                        // warp-uniform
+            const int t = __ffs(act) - 1;
             act &= act - 1;
-            int tb_ = 32;                                        // no second bucket: the upper half idles
-            if (act) { tb_ = __ffs(act) - 1; act &= act - 1; }
-            const int tm = hi ? tb_ : ta;
-            const int p = ((warp + NW * (q * 32 + tm)) << 5) + sub;
+            const int p = ((warp + NW * (q * 32 + t)) << 6) + (lane << 1);
             unsigned nb = 0u;
-            if (tm < 32 && p < HW) {                             // H*W is even: both pixels or none
+            if (p < HW) {                                      // H*W is even: both pixels or none
               const uint2 told = *reinterpret_cast<const uint2*>(temp + p);
               const float2 r = __ldg(reinterpret_cast<const float2*>(rg + p));
               const float2* l2 = reinterpret_cast<const float2*>(lut + (size_t)p * 3);
@@ -1000,10 +1016,8 @@ segment_fps_pair_kernel(const float* __restrict__ range, const float* __restrict
                                                                  __float_as_uint(nb_) | (told.y & 0x80000000u));
               nb = max(__float_as_uint(na), __float_as_uint(nb_));
             }
-            const unsigned ma = __reduce_max_sync(0xffffffffu, hi ? 0u : nb);
-            const unsigned mb = __reduce_max_sync(0xffffffffu, hi ? nb : 0u);
-            bmax[q] = lane == ta ? ma : bmax[q];
-            bmax[q] = lane == tb_ ? mb : bmax[q];
+            const unsigned newmax = __reduce_max_sync(0xffffffffu, nb);
+            bmax[q] = lane == t ? newmax : bmax[q];
           }
         }
       };
@@ -1013,14 +1027,14 @@ segment_fps_pair_kernel(const float* __restrict__ range, const float* __restrict
   }
 }
 
-template <int Q>
-static int launch_fps_pair(const float* range, const float* lut, const float* ground, int B, int HW, int m, float thr,
+template <int THREADS, int Q, int MINB>
+static int launch_fps_wide(const float* range, const float* lut, const float* ground, int B, int HW, int m, float thr,
                            int* center_idx, float* centers, cudaStream_t st) {
-  auto kern = segment_fps_pair_kernel<Q>;
-  const size_t smem = sizeof(float) * 6 * Q * 1024;
+  auto kern = segment_fps_wide_kernel<THREADS, Q, MINB>;
+  const size_t smem = sizeof(float) * 6 * Q * THREADS;
   RPCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  RPCC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 1024, smem));
+  RPCC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
   if (per_sm < 1) per_sm = 1;
   int grid = per_sm * sm_count();
   if (grid > B) grid = B;
@@ -1039,7 +1053,7 @@ static int launch_fps_pair(const float* range, const float* lut, const float* gr
   cudaError_t le = cudaMemsetAsync(counter, 0, sizeof(int), st);
   if (le == cudaSuccess) le = launch_first_pass(range, lut, ground, B, HW, NB, thr, static_cast<unsigned*>(ws), rec, st);
   if (le == cudaSuccess) {
-    kern<<<grid, 1024, smem, st>>>(range, lut, ground, B, HW, m, thr, static_cast<unsigned*>(ws), rec, counter, center_idx, centers);
+    kern<<<grid, THREADS, smem, st>>>(range, lut, ground, B, HW, m, thr, static_cast<unsigned*>(ws), rec, counter, center_idx, centers);
     le = cudaGetLastError();
   }
   RPCC_CUDA(cudaFreeAsync(ws, st));
@@ -1114,12 +1128,17 @@ extern "C" int rpcc_segment_fps_batch(const float* range, const float* lut, cons
     cudaStream_t st = as_stream(stream);
     const int NB = (HW + 31) / 32;
     static const int minb = getenv("RPCC_FPS_MINB") ? atoi(getenv("RPCC_FPS_MINB")) : 2;
-    static const bool pair = !(getenv("RPCC_FPS_PAIR") && atoi(getenv("RPCC_FPS_PAIR")) == 0);
-    if (pair && NB <= 4096 && HW % 2 == 0 && (reinterpret_cast<uintptr_t>(range) | reinterpret_cast<uintptr_t>(lut)) % 8 == 0) {
-      const int q = (NB + 1023) / 1024;
-      if (q <= 1) return launch_fps_pair<1>(range, lut, ground, B, HW, m, ground_thr, center_idx, centers, st);
-      if (q <= 2) return launch_fps_pair<2>(range, lut, ground, B, HW, m, ground_thr, center_idx, centers, st);
-      return launch_fps_pair<4>(range, lut, ground, B, HW, m, ground_thr, center_idx, centers, st);
+    static const bool wide_ok = !(getenv("RPCC_FPS_WIDE") && atoi(getenv("RPCC_FPS_WIDE")) == 0);   // 0: the 32-pixel kernel (A/B, tests)
+    const int NB2 = (HW + 63) / 64;
+    if (wide_ok && NB2 <= 2048 && HW % 2 == 0 && (reinterpret_cast<uintptr_t>(range) | reinterpret_cast<uintptr_t>(lut)) % 8 == 0) {
+      if (fps_threads == 512) {                              // A/B: four CTAs of 512 threads per SM
+        const int q = (NB2 + 511) / 512;
+        if (q <= 1) return launch_fps_wide<512, 1, 4>(range, lut, ground, B, HW, m, ground_thr, center_idx, centers, st);
+        if (q <= 2) return launch_fps_wide<512, 2, 4>(range, lut, ground, B, HW, m, ground_thr, center_idx, centers, st);
+        return launch_fps_wide<512, 4, 4>(range, lut, ground, B, HW, m, ground_thr, center_idx, centers, st);
+      }
+      if (NB2 <= 1024) return launch_fps_wide<1024, 1, 2>(range, lut, ground, B, HW, m, ground_thr, center_idx, centers, st);
+      return launch_fps_wide<1024, 2, 2>(range, lut, ground, B, HW, m, ground_thr, center_idx, centers, st);
     }
     static const bool split = !(getenv("RPCC_FPS_SPLIT") && atoi(getenv("RPCC_FPS_SPLIT")) == 0);
 #define RPCC_FPS_GO(T, Q, M) return split ? launch_fps_pruned<T, Q, M, true>(range, lut, ground, B, HW, m, ground_thr, center_idx, centers, st) \
