@@ -816,6 +816,10 @@ __device__ __forceinline__ unsigned fps_tie_key(unsigned p) { return (__brev(p) 
 //      per step 2.70 ms, two per step (16 lanes x 2 pixels each) 2.43-2.47 ms, 64-pixel buckets 2.26 ms at two CTAs of
 //      1024 threads per SM -- and 2.51 ms at FOUR CTAs of 512 threads (a third fewer instructions, 46 % issue
 //      utilisation): what shortens a round is warps working on the same frame, not more frames per SM.
+//      Also measured (profiles/r02j_fps_wide_smemcoords_ab.txt): the point holding every bucket's maximum kept in shared
+//      memory (first pass and update steps leave it), so that all warps reduce the candidates themselves -- one barrier
+//      per round, no global load before the box tests.  Seeds identical, but a third more instructions (the capture in
+//      every update step, the redundant reduction) at the same 63 % issue utilisation: 2.57-2.66 ms.  Not kept.
 template <int THREADS, int Q, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 segment_fps_wide_kernel(const float* __restrict__ range, const float* __restrict__ lut, const float* __restrict__ ground,
