@@ -59,7 +59,7 @@ def parse():
                          "so a long launch evens out the frame-to-frame spread of the FPS work)")
     ap.add_argument("--e2e-frames", type=int, default=1184)
     ap.add_argument("--host-chunk", type=int, default=0,
-                    help="frames per upload/kernels/download pipeline stage of encode_host (0 = one per SM)")
+                    help="frames per upload/kernels/download pipeline stage of encode_host (0 = three quarters of a frame per SM)")
     ap.add_argument("--datalist-frames", type=int, default=8192, help="files of the config-5 run, all ranks together (0 = skip)")
     ap.add_argument("--datalist-batch", type=int, default=592)
     ap.add_argument("--no-numa-bind", action="store_true", help="leave the process on whatever CPUs the launcher gave it")

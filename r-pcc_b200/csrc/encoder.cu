@@ -260,7 +260,10 @@ extern "C" int rpcc_encoder_create(const rpcc_encoder_config* cfg, rpcc_encoder*
   {
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device) != cudaSuccess) { cudaGetLastError(); sms = 0; }
-    const int want = cfg->host_chunk > 0 ? cfg->host_chunk : (sms > 0 ? sms : cfg->max_batch);
+    // default: three quarters of a frame per SM -- measured on 1184-frame calls (profiles/r02k_host_chunk.txt): 74 or 111
+    // frames per stage 37.0 k frames/s, 148: 36.3 k, 296: 34.1 k (the last stage's kernels and download run with the
+    // upload link idle, so short stages cost less at the end of a call)
+    const int want = cfg->host_chunk > 0 ? cfg->host_chunk : (sms > 0 ? (3 * sms) / 4 : cfg->max_batch);
     e->host_chunk = want < cfg->max_batch ? want : cfg->max_batch;
   }
   // the pybind boundary narrows the Python doubles to float (cpp_modules.cpp:427-428)
