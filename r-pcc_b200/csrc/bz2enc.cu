@@ -389,6 +389,7 @@ extern "C" int rpcc_bz2_compress(const uint8_t* src, size_t n, uint8_t* dst, siz
     static thread_local unsigned char len[kGroups][kMaxAlpha];
     static thread_local int code[kGroups][kMaxAlpha];
     static thread_local int rfreq[kGroups][kMaxAlpha];
+    static thread_local int rfreq2[kGroups][kMaxAlpha];      // (all zero between uses)
     static thread_local unsigned char selector[kMaxSelectors], selectorMtf[kMaxSelectors];
     for (int t = 0; t < kGroups; ++t) for (int v = 0; v < alphaSize; ++v) len[t][v] = 15;
     const int nGroups = nMTF < 200 ? 2 : nMTF < 600 ? 3 : nMTF < 1200 ? 4 : nMTF < 2400 ? 5 : 6;
@@ -430,11 +431,19 @@ extern "C" int rpcc_bz2_compress(const uint8_t* src, size_t n, uint8_t* dst, siz
           if (c < bc) { bc = c; bt = t; }
         }
         selector[nSelectors++] = (unsigned char)bt;
+        // two sets of counters, alternate symbols: consecutive symbols are often the same one (RUNA, 1, 2), and a single
+        // counter then serialises on its own store-to-load latency
         int* rf = rfreq[bt];
-        for (int q = gs; q <= ge; ++q) ++rf[mtfv[q]];
+        int* rg2 = rfreq2[bt];
+        int q = gs;
+        for (; q + 1 <= ge; q += 2) { ++rf[mtfv[q]]; ++rg2[mtfv[q + 1]]; }
+        if (q <= ge) ++rf[mtfv[q]];
         gs = ge + 1;
       }
-      for (int t = 0; t < nGroups; ++t) make_code_lengths(len[t], rfreq[t], alphaSize, 17);
+      for (int t = 0; t < nGroups; ++t) {
+        for (int v = 0; v < alphaSize; ++v) { rfreq[t][v] += rfreq2[t][v]; rfreq2[t][v] = 0; }
+        make_code_lengths(len[t], rfreq[t], alphaSize, 17);
+      }
     }
     {
       unsigned char pos[kGroups];

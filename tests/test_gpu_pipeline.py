@@ -172,6 +172,34 @@ def test_encoder_batches_match_oracle_and_roundtrip(R, lidar, nonuniform):
         assert float(np.abs(rec - wants[b]["range_image"]).max()) <= bound + 1e-5
 
 
+@pytest.mark.parametrize("lidar,accuracy,clusters,nonuniform", [
+    ("Velodyne64E", 0.005, 20, False), ("Velodyne64E", 0.05, 250, False), ("Velodyne64E", 0.01, 37, True),
+    ("VelodyneVLP16", 0.05, 250, True), ("Velodyne32E", 0.005, 64, False)])
+def test_encoder_other_accuracies_and_cluster_counts(R, lidar, accuracy, clusters, nonuniform):
+    """Off the default configuration: --accuracy 0.005 ... 0.05 and --cluster_num 20 ... 250 (the u8 label limit is 252):
+    other centre counts per lane in the label kernel, other table sizes in the quantiser, int16 symbols near their
+    range at the fine step.  Every section byte-exact against the oracle, ground injected and fitted on the device."""
+    from rpcc_b200 import synthetic
+    from rpcc_b200.batch import BatchEncoder
+    from rpcc_b200.config import load_compressor_cfg
+    cfg = load_compressor_cfg()
+    cfg["cluster_num"] = clusters
+    seeds = [40, 41, 42]
+    pts, off, grounds = synthetic.batch(seeds, lidar)
+    H, W, hf, vmax, vmin = oracle.lidar_params(lidar)
+    lut = oracle.transform_map(H, W, hf, vmax, vmin)
+    with BatchEncoder(lidar, accuracy=accuracy, nonuniform=nonuniform, compressor_cfg=cfg, max_batch=2) as enc:
+        for inject in (True, False):
+            out = enc.encode_host(pts, off, grounds if inject else None)
+            for b in range(len(seeds)):
+                p = pts[off[b]:off[b + 1]]
+                g = grounds[b] if inject else oracle.ground_fit(oracle.project(p, H, W, hf, vmax, vmin), lut)
+                want = oracle.compress_frame(p, lidar, g, accuracy=accuracy, nonuniform=nonuniform, cluster_num=clusters)
+                got = BatchEncoder.frame_sections(out, b)
+                for k, v in want["sections"].items():
+                    assert got[k] == v, (lidar, accuracy, clusters, nonuniform, inject, b, k)
+
+
 @pytest.mark.parametrize("lidar,nonuniform,B", [("Velodyne64E", False, 700), ("VelodyneVLP16", True, 1300)])
 def test_long_launch_every_cta_takes_several_frames(R, lidar, nonuniform, B):
     """BASELINE full size and beyond: one launch of B frames (more than the 2 x 148 CTAs of the one-CTA-per-frame
