@@ -232,6 +232,30 @@ def test_segment_fps_and_labels(T, R, lidar):
         assert np.array_equal(labels[b].cpu().numpy().astype(np.int64), seg_t), (lidar, b)
 
 
+@pytest.mark.parametrize("lidar,count", [("Velodyne64E", 64), ("Velodyne32E", 48)])
+def test_segment_fps_many_frames_against_the_reference_kernel(T, R, lidar, count):
+    """Seeds of many distinct frames in one launch against the reference's own kernel (one launch as well): the rare
+    paths of the round kernel -- ties, buckets that die, frames that take several CTAs' worth of time -- get their
+    chance to show up."""
+    import refimpl
+    if not ref.have_cuda():
+        pytest.skip("oracle/_ref/libref_fps.so not shipped")
+    pts, off, grounds = _frames(R, lidar, list(range(300, 300 + count)))
+    cfg, rng = _project_dev(T, R, pts, off, lidar)
+    d_lut = T.from_numpy(cfg.transform_map()).cuda()
+    d_g = T.from_numpy(grounds.astype(np.float32)).cuda()
+    cidx, centers = R.device_mod.segment_fps_batch(rng, d_lut, d_g, 100, 0.1)
+    # the reference's masked cloud (utils/segment_utils.py:137-141), torch's own arithmetic
+    pc = rng.unsqueeze(-1) * d_lut.unsqueeze(0)                                  # (B, H, W, 3)
+    pp = d_g.view(-1, 1, 1, 4)
+    dif = T.abs(T.sum(pc * pp[..., :3], -1) + pp[..., 3]) / T.norm(pp[..., :3], 2, -1)
+    masked = (pc * (dif > 0.1).unsqueeze(-1)).reshape(count, -1, 3).contiguous()
+    want = refimpl.ref_fps_gpu(masked, 100)
+    T.cuda.synchronize()
+    assert T.equal(cidx, want), [int(b) for b in T.nonzero((cidx != want).any(1)).flatten()[:8]]
+    assert T.equal(centers, T.gather(masked, 1, want.long().unsqueeze(-1).expand(-1, -1, 3)))
+
+
 def test_segment_fps_when_seed_zero_is_a_real_point(T, R):
     """The FPS kernel has two update paths: the usual one (pixel 0 is a ground / empty pixel, so every masked point sits
     at distance zero from seed 0 for good) and the general one, taken when pixel 0 survives the ground mask -- then the
