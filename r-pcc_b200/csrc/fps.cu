@@ -435,11 +435,13 @@ __device__ __forceinline__ FpsBucket fps_first_bucket(const float* __restrict__ 
 
 __global__ void __launch_bounds__(kFirstThreads)
 fps_first_pass_kernel(const float* __restrict__ range, const float* __restrict__ lut, const float* __restrict__ ground,
-                      int B, int HW, int NB, int runs, float thr, unsigned* __restrict__ temp_ws, FpsBucket* __restrict__ rec) {
+                      int B, int HW, int NB, int runs, float thr, unsigned* __restrict__ temp_ws, FpsBucket* __restrict__ rec,
+                      int* __restrict__ work) {
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * (kFirstThreads / 32) + (threadIdx.x >> 5);
   const int f = w / runs, c = w - f * runs;
   if (f >= B) return;                                        // warp-uniform
+  int nlive = 0;                                             // buckets of this warp's run that can still change
   const int per = (NB + runs - 1) / runs;
   const int b0 = c * per, b1 = min(NB, b0 + per);
   const float* rg = range + (size_t)f * HW;
@@ -451,12 +453,14 @@ fps_first_pass_kernel(const float* __restrict__ range, const float* __restrict__
 #pragma unroll 2
   for (int b = b0; b < b1; ++b) {
     const FpsBucket o = fps_first_bucket(rg, lut, b, lane, HW, g0, g1, g2, g3, gnorm, thr, x1, y1, z1, temp);
+    nlive += o.bmax != 0u ? 1 : 0;
     if (lane == 0) {
       float4* dst = reinterpret_cast<float4*>(rec + (size_t)f * NB + b);
       dst[0] = make_float4(o.x0, o.y0, o.z0, o.x1);
       dst[1] = make_float4(o.y1, o.z1, __uint_as_float(o.bmax), __uint_as_float(o.btk));
     }
   }
+  if (work && lane == 0 && nlive) atomicAdd(work + f, nlive);
 }
 
 // The same with four consecutive pixels per lane (H*W a multiple of 4): 128-bit loads and stores, a bucket is 8 lanes, a warp
@@ -482,11 +486,13 @@ __device__ __forceinline__ unsigned seg8_umax(unsigned v) {
 
 __global__ void __launch_bounds__(kFirstThreads)
 fps_first_pass4_kernel(const float* __restrict__ range, const float* __restrict__ lut, const float* __restrict__ ground,
-                       int B, int HW, int NB, int runs, float thr, unsigned* __restrict__ temp_ws, FpsBucket* __restrict__ rec) {
+                       int B, int HW, int NB, int runs, float thr, unsigned* __restrict__ temp_ws, FpsBucket* __restrict__ rec,
+                       int* __restrict__ work) {
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * (kFirstThreads / 32) + (threadIdx.x >> 5);
   const int f = w / runs, c = w - f * runs;
   if (f >= B) return;                                        // warp-uniform
+  int nlive = 0;                                             // buckets of this warp's run that can still change
   const int NG = (HW + 127) >> 7;                            // groups of 4 buckets
   const int per = (NG + runs - 1) / runs;
   const int ga = c * per, gb = min(NG, ga + per);
@@ -540,6 +546,7 @@ fps_first_pass4_kernel(const float* __restrict__ range, const float* __restrict_
     const unsigned t2 = inb ? __float_as_uint(t[2]) : 0u, t3 = inb ? __float_as_uint(t[3]) : 0u;
     const unsigned bmax = seg8_umax(max(max(t0, t1), max(t2, t3)));
     const int b = (g << 2) + (lane >> 3);                    // this lane's bucket
+    nlive += __popc(__ballot_sync(0xffffffffu, (lane & 7) == 0 && b < NB && bmax != 0u));
     FpsBucket o = {INF, INF, INF, -INF, -INF, -INF, 0u, kNoTie};
     // buckets whose running distances are all zero stay at the defaults (see fps_first_bucket); bucket 0 is always kept
     if (__any_sync(0xffffffffu, bmax != 0u) || g == 0) {
@@ -572,6 +579,29 @@ fps_first_pass4_kernel(const float* __restrict__ range, const float* __restrict_
       dst[1] = make_float4(o.y1, o.z1, __uint_as_float(o.bmax), __uint_as_float(o.btk));
     }
   }
+  if (work && lane == 0 && nlive) atomicAdd(work + f, nlive);
+}
+
+// The round kernels give one frame at a time to a CTA, and a frame's rounds cost in proportion to its buckets that can
+// change (30 ... 60 % of them).  Handing the frames out longest first keeps the CTAs' finishing times together: queue[i] =
+// the frame with the i-th largest count (ties by index; any order gives the same seeds), followed by `tail` entries B that
+// send the CTAs home.  work == nullptr: index order.
+constexpr int kOrderMaxFrames = 8192;
+__global__ void __launch_bounds__(256)
+fps_order_kernel(const int* __restrict__ work, int B, int tail, int* __restrict__ queue) {
+  const int f = blockIdx.x * 256 + threadIdx.x;
+  if (f >= B + tail) return;
+  if (f >= B) { queue[f] = B; return; }
+  int rank = f;
+  if (work) {
+    const int w = work[f];
+    rank = 0;
+    for (int g = 0; g < B; ++g) {
+      const int v = __ldg(work + g);
+      rank += (v > w || (v == w && g < f)) ? 1 : 0;
+    }
+  }
+  queue[rank] = f;
 }
 
 template <int THREADS, int Q, int MINB, bool SPLIT>   // Q buckets per lane: the warp owns buckets warp + NW * (q * 32 + lane)
@@ -788,14 +818,14 @@ segment_fps_pruned_kernel(const float* __restrict__ range, const float* __restri
 }
 
 static cudaError_t launch_first_pass(const float* range, const float* lut, const float* ground, int B, int HW, int NB, float thr,
-                                     unsigned* temp_ws, FpsBucket* rec, cudaStream_t st) {
+                                     unsigned* temp_ws, FpsBucket* rec, cudaStream_t st, int* work = nullptr) {
   const int runs = 32;                                       // warps per frame: ~125 buckets each at 64 x 2000
   const long long warps = (long long)B * runs;
   const int wpb = kFirstThreads / 32;
   const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
   const bool vec4 = HW % 4 == 0 && (reinterpret_cast<uintptr_t>(range) | reinterpret_cast<uintptr_t>(lut)) % 16 == 0;
-  if (vec4) fps_first_pass4_kernel<<<blocks, kFirstThreads, 0, st>>>(range, lut, ground, B, HW, NB, runs, thr, temp_ws, rec);
-  else fps_first_pass_kernel<<<blocks, kFirstThreads, 0, st>>>(range, lut, ground, B, HW, NB, runs, thr, temp_ws, rec);
+  if (vec4) fps_first_pass4_kernel<<<blocks, kFirstThreads, 0, st>>>(range, lut, ground, B, HW, NB, runs, thr, temp_ws, rec, work);
+  else fps_first_pass_kernel<<<blocks, kFirstThreads, 0, st>>>(range, lut, ground, B, HW, NB, runs, thr, temp_ws, rec, work);
   count_launch();
   return cudaGetLastError();
 }
@@ -838,7 +868,8 @@ segment_fps_wide_kernel(const float* __restrict__ range, const float* __restrict
   const float INF = __int_as_float(0x7f800000);
 
   for (;;) {
-    if (tid == 0) s_frame = atomicAdd(next_frame, 1);
+    // queue: next_frame[0] = head, next_frame[64 ...] = the frames, longest first, then one B per CTA (fps_order_kernel)
+    if (tid == 0) s_frame = next_frame[64 + atomicAdd(next_frame, 1)];
     __syncthreads();
     const int f = s_frame;
     if (f >= B) break;
@@ -1050,12 +1081,22 @@ static int launch_fps_wide(const float* range, const float* lut, const float* gr
   const size_t rec_bytes = sizeof(FpsBucket) * (size_t)B * NB;
   const size_t rec_off = (temp_bytes + 255) & ~(size_t)255;
   const size_t ctr_off = rec_off + ((rec_bytes + 255) & ~(size_t)255);
-  RPCC_CUDA(cudaMallocFromPoolAsync(&ws, ctr_off + 256, pool, st));
+  static const bool order_ok = !(getenv("RPCC_FPS_ORDER") && atoi(getenv("RPCC_FPS_ORDER")) == 0);   // 0: frames in index order (A/B)
+  const bool ordered = order_ok && B > grid && B <= kOrderMaxFrames;      // more frames than CTAs: longest first
+  RPCC_CUDA(cudaMallocFromPoolAsync(&ws, ctr_off + 256 + sizeof(int) * ((size_t)2 * B + grid), pool, st));
   unsigned char* base = static_cast<unsigned char*>(ws);
   FpsBucket* rec = reinterpret_cast<FpsBucket*>(base + rec_off);
-  int* counter = reinterpret_cast<int*>(base + ctr_off);
-  cudaError_t le = cudaMemsetAsync(counter, 0, sizeof(int), st);
-  if (le == cudaSuccess) le = launch_first_pass(range, lut, ground, B, HW, NB, thr, static_cast<unsigned*>(ws), rec, st);
+  int* counter = reinterpret_cast<int*>(base + ctr_off);     // queue head (256 bytes), the queue (B + grid entries), live buckets per frame (B)
+  int* queue = counter + 64;
+  int* work = queue + B + grid;
+  cudaError_t le = cudaMemsetAsync(counter, 0, 256, st);
+  if (le == cudaSuccess && ordered) le = cudaMemsetAsync(work, 0, sizeof(int) * (size_t)B, st);
+  if (le == cudaSuccess) le = launch_first_pass(range, lut, ground, B, HW, NB, thr, static_cast<unsigned*>(ws), rec, st, ordered ? work : nullptr);
+  if (le == cudaSuccess) {
+    fps_order_kernel<<<(B + grid + 255) / 256, 256, 0, st>>>(ordered ? work : nullptr, B, grid, queue);
+    le = cudaGetLastError();
+    count_launch();
+  }
   if (le == cudaSuccess) {
     kern<<<grid, THREADS, smem, st>>>(range, lut, ground, B, HW, m, thr, static_cast<unsigned*>(ws), rec, counter, center_idx, centers);
     le = cudaGetLastError();
