@@ -589,19 +589,27 @@ fps_first_pass4_kernel(const float* __restrict__ range, const float* __restrict_
 constexpr int kOrderMaxFrames = 8192;
 __global__ void __launch_bounds__(256)
 fps_order_kernel(const int* __restrict__ work, int B, int tail, int* __restrict__ queue) {
+  __shared__ int s_w[256];
   const int f = blockIdx.x * 256 + threadIdx.x;
-  if (f >= B + tail) return;
-  if (f >= B) { queue[f] = B; return; }
-  int rank = f;
-  if (work) {
-    const int w = work[f];
-    rank = 0;
-    for (int g = 0; g < B; ++g) {
-      const int v = __ldg(work + g);
-      rank += (v > w || (v == w && g < f)) ? 1 : 0;
+  if (work == nullptr) {                                     // index order
+    if (f < B + tail) queue[f] = f < B ? f : B;
+    return;
+  }
+  const int w = f < B ? work[f] : 0;
+  int rank = 0;
+  for (int g0 = 0; g0 < B; g0 += 256) {                      // every thread of the block walks the same counts: a tile at a time
+    __syncthreads();
+    s_w[threadIdx.x] = g0 + (int)threadIdx.x < B ? work[g0 + threadIdx.x] : -1;
+    __syncthreads();
+    const int n = min(256, B - g0);
+#pragma unroll 8
+    for (int i = 0; i < n; ++i) {
+      const int v = s_w[i];
+      rank += (v > w || (v == w && g0 + i < f)) ? 1 : 0;
     }
   }
-  queue[rank] = f;
+  if (f < B) queue[rank] = f;
+  else if (f < B + tail) queue[f] = B;
 }
 
 template <int THREADS, int Q, int MINB, bool SPLIT>   // Q buckets per lane: the warp owns buckets warp + NW * (q * 32 + lane)
