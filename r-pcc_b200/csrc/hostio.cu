@@ -119,12 +119,16 @@ int pack_one(const Bz2* bz, const Job& j, std::vector<unsigned char>& out, std::
     if (tmp.size() < cap) tmp.resize(cap);
     unsigned got = cap;
     const int slot = s + (5 - j.nsec);               // the last four sections line up whether or not salience leads
-    // mode 0: every 256th frame of a worker codes the section with BOTH coders (same input, so the two costs compare
-    // like with like) and keeps the running costs; in between the cheaper one is used
+    // mode 0: now and then a worker codes the section with BOTH coders (same input, so the two costs compare like with
+    // like) and keeps the running costs; in between the cheaper one is used.  A worker's very first section is not a
+    // probe: the own encoder grows its scratch buffers on that call, and a first probe taken cold sent the worker to
+    // libbz2 for its next 255 frames (measured on 4096 files: 783 frames/s against 915 with the own encoder forced).
+    // Probes: frames 1, 16, then every 256th.
     bool probe = false;
     int use = mode == 1 ? 1 : 0;                     // 0 = own, 1 = libbz2
     if (mode == 0) {
-      probe = (st.seen[slot]++ & 255u) == 0 && n >= 512;
+      const unsigned k = st.seen[slot]++;
+      probe = (k == 1u || k == 16u || (k > 0u && (k & 255u) == 0u)) && n >= 512;
       use = st.cost[1][slot] < st.cost[0][slot] ? 1 : 0;
     }
     int rc = RPCC_BZ2_DECLINED;
