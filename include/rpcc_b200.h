@@ -383,6 +383,11 @@ RPCC_API int rpcc_packer_wait(rpcc_packer* pk, long long ticket);
  * leaves to libbz2 -- more than one block, or a block made of repetitions of a shorter string) or RPCC_ERR_CAPACITY. */
 #define RPCC_BZ2_DECLINED 1
 RPCC_API int rpcc_bz2_compress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_len);
+/* The inverse (BasicCompressor.bzip2_decompress = bz2.decompress, utils/compress_utils.py:300-302): the decoded bytes of
+ * the .bz2 stream src[0..n) into dst.  Table-driven Huffman decoding, 64-bit bit buffer; both CRCs are checked.  Returns
+ * RPCC_OK, RPCC_BZ2_DECLINED (a randomised block or a stream this decoder finds malformed: give it to libbz2, whose
+ * verdict then counts) or RPCC_ERR_CAPACITY.  rpcc_unpack_rpcc uses it first (environment RPCC_BZ2_DECODER = own | libbz2). */
+RPCC_API int rpcc_bz2_decompress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t* out_len);
 /* dataset/dataset.py:57-63 for a KITTI .bin (rows of x,y,z,intensity f32): the xyz columns into dst (room for
  * cap_rows rows of 3 floats, typically a slice of the pinned upload buffer); *rows_out = rows in the file. */
 RPCC_API int rpcc_read_bin_xyz(const char* path, float* dst, int64_t cap_rows, int64_t* rows_out);

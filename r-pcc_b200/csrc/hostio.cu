@@ -373,8 +373,15 @@ extern "C" int rpcc_unpack_rpcc(const uint8_t* blob, size_t n, int uniform, uint
     at += 4;
     if (len < 0 || at + (size_t)len > n) { set_error("rpcc_unpack_rpcc: bad section length"); return RPCC_ERR_ARG; }
     unsigned got = (unsigned)((cap - out) > 0xffffffffu ? 0xffffffffu : (cap - out));
-    const int rc = bz->decompress(reinterpret_cast<char*>(dst + out), &got, reinterpret_cast<char*>(const_cast<uint8_t*>(blob + at)), (unsigned)len, 0, 0);
-    if (rc != 0) { set_error("rpcc_unpack_rpcc: section %d does not decode (libbz2 %d)", s, rc); return rc == -8 ? RPCC_ERR_CAPACITY : RPCC_ERR_ARG; }
+    // this library's decoder first (bz2dec.cu); what it declines -- and every error verdict -- is libbz2's
+    static const bool own_first = !(getenv("RPCC_BZ2_DECODER") && !strcmp(getenv("RPCC_BZ2_DECODER"), "libbz2"));
+    size_t got2 = 0;
+    if (own_first && rpcc_bz2_decompress(blob + at, (size_t)len, dst + out, got, &got2) == RPCC_OK) {
+      got = (unsigned)got2;
+    } else {
+      const int rc = bz->decompress(reinterpret_cast<char*>(dst + out), &got, reinterpret_cast<char*>(const_cast<uint8_t*>(blob + at)), (unsigned)len, 0, 0);
+      if (rc != 0) { set_error("rpcc_unpack_rpcc: section %d does not decode (libbz2 %d)", s, rc); return rc == -8 ? RPCC_ERR_CAPACITY : RPCC_ERR_ARG; }
+    }
     sec_len[s] = got;
     out += got;
     at += (size_t)len;

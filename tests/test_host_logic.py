@@ -257,6 +257,47 @@ def test_own_bzip2_encoder_writes_libbz2_bytes():
     assert _own_bz2(rng.integers(0, 256, 950000).astype(np.uint8).tobytes())[0] == 1
 
 
+def _own_unbz2(stream, cap):
+    import ctypes as C
+    import rpcc_b200
+    dst = C.create_string_buffer(max(cap, 1))
+    n = C.c_size_t(0)
+    rc = rpcc_b200.lib().rpcc_bz2_decompress(bytes(stream), C.c_size_t(len(stream)), dst, C.c_size_t(cap), C.byref(n))
+    return rc, dst.raw[:n.value]
+
+
+def test_own_bzip2_decoder_inverts_libbz2():
+    """csrc/bz2dec.cu must return what bz2.decompress returns (the reference's decoder, utils/compress_utils.py:300-302)
+    for every stream bz2.compress writes: all levels, empty input, run-length edge cases, several blocks, every section of
+    real frames; it must refuse (1, the caller then asks libbz2) a damaged stream or a bad CRC, and report a short
+    destination."""
+    import bz2
+    from rpcc_b200 import synthetic
+    rng = np.random.default_rng(12)
+    cases = [b"", b"a", b"aaaa", b"aaaaa", b"a" * 259, b"a" * 260, b"a" * 1000, bytes(range(256)) * 10, b"ab" * 5000,
+             b"\x00" * 70000 + b"\x01"]
+    for n in (5, 199, 600, 2400, 10000, 70000):
+        cases.append(rng.integers(0, 256, n).astype(np.uint8).tobytes())
+        cases.append(rng.integers(0, 3, n).astype(np.uint8).tobytes())
+        cases.append(rng.integers(-30, 30, n // 2 + 1).astype(np.int16).tobytes())
+        cases.append(np.repeat(rng.integers(0, 100, n // 7 + 1), rng.integers(1, 600, n // 7 + 1)).astype(np.uint8).tobytes()[:n])
+    cases.append(rng.normal(0, 20, 1_100_000).round().astype(np.int16).tobytes())            # three blocks at level 9
+    for lidar in ("Velodyne64E", "VelodyneVLP16"):
+        p, g = synthetic.frame(6, lidar)
+        cases.extend(bytes(v) for v in oracle.compress_frame(p, lidar, g, nonuniform=True)["sections"].values())
+    for i, c in enumerate(cases):
+        for level in ((9, 1 + i % 8) if len(c) < 200000 else (9,)):
+            rc, out = _own_unbz2(bz2.compress(c, level), len(c) + 8)
+            assert rc == 0 and out == c, (i, len(c), level, rc)
+    good = bz2.compress(cases[-1])
+    assert _own_unbz2(good, len(cases[-1]) - 1)[0] < 0                         # destination too small
+    bad = bytearray(good)
+    bad[len(bad) // 2] ^= 0x10
+    assert _own_unbz2(bytes(bad), len(cases[-1]) + 8)[0] != 0                  # damaged: declined, never "ok"
+    assert _own_unbz2(good[:len(good) // 2], len(cases[-1]) + 8)[0] == 1       # truncated
+    assert _own_unbz2(b"BZh9" + b"\x00" * 20, 100)[0] == 1 and _own_unbz2(b"not a stream", 100)[0] == 1
+
+
 @pytest.mark.parametrize("coder", ["auto", "own", "libbz2"])
 def test_packer_coders_agree(tmp_path, monkeypatch, coder):
     """The entropy pool may use libbz2, the library's own encoder, or whichever it measures as cheaper per section: the
