@@ -14,6 +14,9 @@
 // Both CRCs are checked.  tests/test_host_logic.py decodes thousands of bz2.compress outputs and compares.
 #include <stdlib.h>
 #include <string.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <vector>
 
@@ -23,17 +26,29 @@ namespace {
 
 constexpr int kMaxAlpha = 258, kGroups = 6, kGroupSize = 50, kMaxSelectors = 18002, kFastBits = 11;
 
+// bzip2's CRC (MSB-first, polynomial 0x04c11db7), four bytes per step: t[k][b] = the CRC of byte b followed by k zero bytes
 struct CrcTable {
-  unsigned t[256];
+  unsigned t[4][256];
   CrcTable() {
     for (unsigned i = 0; i < 256; ++i) {
       unsigned c = i << 24;
       for (int k = 0; k < 8; ++k) c = (c & 0x80000000u) ? (c << 1) ^ 0x04c11db7u : (c << 1);
-      t[i] = c;
+      t[0][i] = c;
     }
+    for (int k = 1; k < 4; ++k)
+      for (unsigned i = 0; i < 256; ++i) t[k][i] = (t[k - 1][i] << 8) ^ t[0][t[k - 1][i] >> 24];
   }
 };
 const CrcTable g_crc;
+inline unsigned crc_update(unsigned crc, const unsigned char* p, size_t n) {
+  while (n >= 4) {
+    crc ^= ((unsigned)p[0] << 24) | ((unsigned)p[1] << 16) | ((unsigned)p[2] << 8) | (unsigned)p[3];
+    crc = g_crc.t[3][crc >> 24] ^ g_crc.t[2][(crc >> 16) & 255u] ^ g_crc.t[1][(crc >> 8) & 255u] ^ g_crc.t[0][crc & 255u];
+    p += 4; n -= 4;
+  }
+  while (n--) crc = (crc << 8) ^ g_crc.t[0][(crc >> 24) ^ *p++];
+  return crc;
+}
 
 // MSB-first bit reader over a byte buffer; past the end it reads zeros, and over() tells whether any of them were consumed
 struct BitReader {
@@ -104,6 +119,10 @@ bool build_table(Table& t, const unsigned char* len, int alphaSize) {
   }
   return true;
 }
+
+// g_mtf_mask + 15 - pos: sixteen bytes, 0xFF at index <= pos
+alignas(16) const unsigned char g_mtf_mask[32] = {255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255,
+                                                  0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
 struct Scratch {
   std::vector<unsigned> tt;
@@ -185,8 +204,8 @@ extern "C" int rpcc_bz2_decompress(const uint8_t* src, size_t n, uint8_t* dst, s
     unsigned* tt = S.tt.data();
     int unzftab[256];
     for (int q = 0; q < 256; ++q) unzftab[q] = 0;
-    unsigned char yy[256];
-    for (int q = 0; q < nInUse; ++q) yy[q] = (unsigned char)q;
+    alignas(16) unsigned char yy[256 + 16];
+    for (int q = 0; q < 256 + 16; ++q) yy[q] = (unsigned char)q;
     int nblock = 0, groupNo = -1, groupPos = 0;
     const Table* T = nullptr;
     int runLen = 0, runBit = 1;                                   // pending zero run: RUNA adds runBit, RUNB 2 * runBit
@@ -234,9 +253,22 @@ extern "C" int rpcc_bz2_decompress(const uint8_t* src, size_t n, uint8_t* dst, s
       {
         const int pos = sym - 1;                                  // 1 .. nInUse - 1
         const unsigned char v = yy[pos];
+#if defined(__SSE2__)
+        if (pos < 16) {
+          // the first 16 entries in one register: shifted up by one where the index is <= pos, the moved value in front
+          const __m128i cur = _mm_load_si128(reinterpret_cast<const __m128i*>(yy));
+          const __m128i sh = _mm_or_si128(_mm_slli_si128(cur, 1), _mm_cvtsi32_si128((int)v));
+          const __m128i m = _mm_loadu_si128(reinterpret_cast<const __m128i*>(g_mtf_mask + 15 - pos));   // 0xFF for index <= pos
+          _mm_store_si128(reinterpret_cast<__m128i*>(yy), _mm_or_si128(_mm_and_si128(sh, m), _mm_andnot_si128(m, cur)));
+        } else {
+          memmove(yy + 1, yy, (size_t)pos);
+          yy[0] = v;
+        }
+#else
         if (pos < 8) { for (int q = pos; q > 0; --q) yy[q] = yy[q - 1]; }
         else memmove(yy + 1, yy, (size_t)pos);
         yy[0] = v;
+#endif
         const unsigned char uc = seqToUnseq[v];
         ++unzftab[uc];
         tt[nblock++] = uc;
@@ -253,7 +285,7 @@ extern "C" int rpcc_bz2_decompress(const uint8_t* src, size_t n, uint8_t* dst, s
         tt[cftab[uc]++] |= (unsigned)i << 8;
       }
     }
-    unsigned crc = 0xffffffffu;
+    const size_t out0 = out;
     unsigned tPos = tt[origPtr] >> 8;
     int run = 0, prev = -1;
     for (int i = 0; i < nblock; ++i) {
@@ -262,16 +294,16 @@ extern "C" int rpcc_bz2_decompress(const uint8_t* src, size_t n, uint8_t* dst, s
       tPos >>= 8;
       if (run == 4) {                                             // a count byte: ch more copies of prev
         if (out + ch > cap) return RPCC_ERR_CAPACITY;
-        for (int q = 0; q < ch; ++q) { dst[out++] = (unsigned char)prev; crc = (crc << 8) ^ g_crc.t[(crc >> 24) ^ (unsigned)prev]; }
+        memset(dst + out, prev, ch);
+        out += ch;
         run = 0; prev = -1;
         continue;
       }
       if (out >= cap) return RPCC_ERR_CAPACITY;
       dst[out++] = ch;
-      crc = (crc << 8) ^ g_crc.t[(crc >> 24) ^ ch];
       if (ch == prev) ++run; else { run = 1; prev = ch; }
     }
-    crc = ~crc;
+    const unsigned crc = ~crc_update(0xffffffffu, dst + out0, out - out0);   // (off the pointer chase's dependency chain)
     if (crc != blockCrc) return RPCC_BZ2_DECLINED;
     combined = ((combined << 1) | (combined >> 31)) ^ crc;
   }
