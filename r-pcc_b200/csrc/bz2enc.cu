@@ -18,6 +18,9 @@
 // with bz2.compress on thousands of inputs.
 #include <stdlib.h>
 #include <string.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <vector>
 #ifdef RPCC_BZ2_PROFILE
@@ -38,6 +41,9 @@ namespace {
 constexpr int kRunA = 0, kRunB = 1;
 constexpr int kMaxAlpha = 258, kGroups = 6, kGroupSize = 50, kIters = 4, kMaxSelectors = 18002;
 constexpr int kBlockMax = 900000 - 19;
+// kMtfMask + 15 - pos: sixteen bytes, 0xFF at index <= pos
+alignas(16) const unsigned char kMtfMask[32] = {255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255,
+                                                0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
 // ------------------------------------------------------------------------------------------------ CRC (bzlib crctable.c)
 struct CrcTable {
@@ -351,8 +357,8 @@ extern "C" int rpcc_bz2_compress(const uint8_t* src, size_t n, uint8_t* dst, siz
     for (int q = 0; q <= EOB; ++q) mtfFreq[q] = 0;
     S.mtfv.resize((size_t)nb + 2);
     unsigned short* mtfv = S.mtfv.data();
-    unsigned char yy[256];
-    for (int q = 0; q < nInUse; ++q) yy[q] = (unsigned char)q;
+    alignas(16) unsigned char yy[256 + 16];                   // (padded: the search below reads 16 entries at a time)
+    for (int q = 0; q < 256 + 16; ++q) yy[q] = (unsigned char)q;
     int wr = 0, zPend = 0;
     auto flush_zeros = [&]() {
       if (zPend > 0) {
@@ -371,11 +377,35 @@ extern "C" int rpcc_bz2_compress(const uint8_t* src, size_t n, uint8_t* dst, siz
       const unsigned char ll = unseqToSeq[block[j]];
       if (yy[0] == ll) { ++zPend; continue; }
       flush_zeros();
+#if defined(__SSE2__)
+      // position of ll in the list, 16 entries per compare; the list is a permutation of the symbols in use, so ll is
+      // found before the padding.  Then the entries in front of it move up by one: inside one register when pos < 16.
+      int pos;
+      {
+        const __m128i key = _mm_set1_epi8((char)ll);
+        int base = 0;
+        for (;;) {
+          const int m = _mm_movemask_epi8(_mm_cmpeq_epi8(_mm_load_si128(reinterpret_cast<const __m128i*>(yy + base)), key));
+          if (m) { pos = base + __builtin_ctz((unsigned)m); break; }
+          base += 16;
+        }
+      }
+      if (pos < 16) {
+        const __m128i cur = _mm_load_si128(reinterpret_cast<const __m128i*>(yy));
+        const __m128i sh = _mm_or_si128(_mm_slli_si128(cur, 1), _mm_cvtsi32_si128((int)ll));
+        const __m128i m = _mm_loadu_si128(reinterpret_cast<const __m128i*>(kMtfMask + 15 - pos));   // 0xFF for index <= pos
+        _mm_store_si128(reinterpret_cast<__m128i*>(yy), _mm_or_si128(_mm_and_si128(sh, m), _mm_andnot_si128(m, cur)));
+      } else {
+        memmove(yy + 1, yy, (size_t)pos);
+        yy[0] = ll;
+      }
+#else
       int pos = 1;
       unsigned char carry = yy[0];
       while (yy[pos] != ll) { const unsigned char t2 = yy[pos]; yy[pos] = carry; carry = t2; ++pos; }
       yy[pos] = carry;
       yy[0] = ll;
+#endif
       mtfv[wr++] = (unsigned short)(pos + 1);
       ++mtfFreq[pos + 1];
     }
