@@ -46,17 +46,29 @@ alignas(16) const unsigned char kMtfMask[32] = {255, 255, 255, 255, 255, 255, 25
                                                 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
 // ------------------------------------------------------------------------------------------------ CRC (bzlib crctable.c)
+// bzip2's CRC (MSB-first, polynomial 0x04c11db7), four bytes per step: t[k][b] = the CRC of byte b followed by k zero bytes
 struct CrcTable {
-  unsigned t[256];
+  unsigned t[4][256];
   CrcTable() {
     for (unsigned i = 0; i < 256; ++i) {
       unsigned c = i << 24;
       for (int k = 0; k < 8; ++k) c = (c & 0x80000000u) ? (c << 1) ^ 0x04c11db7u : (c << 1);
-      t[i] = c;
+      t[0][i] = c;
     }
+    for (int k = 1; k < 4; ++k)
+      for (unsigned i = 0; i < 256; ++i) t[k][i] = (t[k - 1][i] << 8) ^ t[0][t[k - 1][i] >> 24];
   }
 };
 const CrcTable g_crc;
+inline unsigned crc_update(unsigned crc, const unsigned char* p, size_t n) {
+  while (n >= 4) {
+    crc ^= ((unsigned)p[0] << 24) | ((unsigned)p[1] << 16) | ((unsigned)p[2] << 8) | (unsigned)p[3];
+    crc = g_crc.t[3][crc >> 24] ^ g_crc.t[2][(crc >> 16) & 255u] ^ g_crc.t[1][(crc >> 8) & 255u] ^ g_crc.t[0][crc & 255u];
+    p += 4; n -= 4;
+  }
+  while (n--) crc = (crc << 8) ^ g_crc.t[0][(crc >> 24) ^ *p++];
+  return crc;
+}
 
 // ------------------------------------------------------------------------------------------------ suffix sorting (SA-IS)
 // s[0..n): symbols in [0, K), s[n-1] = 0 is the unique smallest one.  SA receives the suffix array.  The string is
@@ -167,18 +179,17 @@ int least_rotation(const unsigned char* s, int n) {
   return i < j ? i : j;
 }
 
-// true if the block is a whole number (>= 2) of repetitions of a shorter string
-bool is_periodic(const unsigned char* s, int n, std::vector<int>& pi) {
-  if (n < 2) return false;
-  pi.resize((size_t)n);
-  pi[0] = 0;
-  for (int i = 1, k = 0; i < n; ++i) {
-    while (k > 0 && s[i] != s[k]) k = pi[k - 1];
-    if (s[i] == s[k]) ++k;
-    pi[i] = k;
+// true if the block is a whole number (>= 2) of repetitions of a shorter string: some proper divisor p of n is a period.
+// (A prefix-function pass over the block answered the same question in 0.6 ms per frame; a mismatch within the first few
+// bytes settles nearly every divisor.)
+bool is_periodic(const unsigned char* s, int n) {
+  for (int d = 1; (long long)d * d <= n; ++d) {
+    if (n % d) continue;
+    const int e = n / d;
+    if (d < n && memcmp(s, s + d, (size_t)(n - d)) == 0) return true;
+    if (e < n && e != d && memcmp(s, s + e, (size_t)(n - e)) == 0) return true;
   }
-  const int p = n - pi[n - 1];
-  return p < n && n % p == 0;
+  return false;
 }
 
 // ------------------------------------------------------------------------------------------------ bit writer (bzlib bsW)
@@ -288,14 +299,12 @@ extern "C" int rpcc_bz2_compress(const uint8_t* src, size_t n, uint8_t* dst, siz
     unsigned char* w = blk.data();
     bool inUse[256];
     memset(inUse, 0, sizeof(inUse));
-    unsigned crc = 0xffffffffu;
+    unsigned crc = crc_update(0xffffffffu, src, n);
     size_t i = 0;
     while (i < n) {
       const unsigned char ch = src[i];
       size_t run = 1;
       while (i + run < n && src[i + run] == ch && run < 255) ++run;
-      const unsigned* tab = g_crc.t;
-      for (size_t q = 0; q < run; ++q) crc = (crc << 8) ^ tab[(crc >> 24) ^ ch];
       inUse[ch] = true;
       if (run < 4) {
         for (size_t q = 0; q < run; ++q) *w++ = ch;
@@ -313,7 +322,7 @@ extern "C" int rpcc_bz2_compress(const uint8_t* src, size_t n, uint8_t* dst, siz
     if (nb > kBlockMax - 1024) return RPCC_BZ2_DECLINED;
     const unsigned char* block = blk.data();
     TICK(0);
-    if (is_periodic(block, nb, S.pi)) return RPCC_BZ2_DECLINED;
+    if (is_periodic(block, nb)) return RPCC_BZ2_DECLINED;
     TICK(1);
     // ---- sorted rotations: suffix array of the least rotation (a Lyndon word) with a sentinel
     const int r = least_rotation(block, nb);
