@@ -165,14 +165,18 @@ void sais(Ch* s, int* SA, int n, int K) {
 }
 
 // start of the lexicographically least rotation
-int least_rotation(const unsigned char* s, int n) {
+// d = the block written twice (2n bytes + 8 of padding): no index ever wraps, and the common prefix of two rotations is
+// measured eight bytes at a time
+int least_rotation(const unsigned char* d, int n) {
   int i = 0, j = 1, k = 0;
   while (i < n && j < n && k < n) {
-    int a = i + k, b = j + k;
-    if (a >= n) a -= n;
-    if (b >= n) b -= n;
-    if (s[a] == s[b]) { ++k; continue; }
-    if (s[a] > s[b]) i += k + 1; else j += k + 1;
+    unsigned long long a, b;
+    memcpy(&a, d + i + k, 8);
+    memcpy(&b, d + j + k, 8);
+    if (a == b) { k += 8; continue; }
+    k += (int)(__builtin_ctzll(a ^ b) >> 3);                  // little-endian: the lowest differing byte comes first
+    if (k >= n) break;
+    if (d[i + k] > d[j + k]) i += k + 1; else j += k + 1;
     if (i == j) ++j;
     k = 0;
   }
@@ -295,7 +299,7 @@ extern "C" int rpcc_bz2_compress(const uint8_t* src, size_t n, uint8_t* dst, siz
     if (n > (size_t)kBlockMax - 1024) return RPCC_BZ2_DECLINED;   // more than one block (or close to it): libbz2's business
     // ---- initial run-length pass (bzlib.c add_pair_to_block) + block CRC over the original bytes
     std::vector<unsigned char>& blk = S.block;
-    blk.resize(n + n / 4 + 16);
+    if (blk.size() < n + n / 4 + 16) blk.resize(n + n / 4 + 16);   // scratch buffers only ever grow: a resize back up would zero-fill
     unsigned char* w = blk.data();
     bool inUse[256];
     memset(inUse, 0, sizeof(inUse));
@@ -315,21 +319,23 @@ extern "C" int rpcc_bz2_compress(const uint8_t* src, size_t n, uint8_t* dst, siz
       }
       i += run;
     }
-    blk.resize((size_t)(w - blk.data()));
+    const size_t blk_len = (size_t)(w - blk.data());
     crc = ~crc;
     combined = ((combined << 1) | (combined >> 31)) ^ crc;
-    const int nb = (int)blk.size();
+    const int nb = (int)blk_len;
     if (nb > kBlockMax - 1024) return RPCC_BZ2_DECLINED;
     const unsigned char* block = blk.data();
     TICK(0);
     if (is_periodic(block, nb)) return RPCC_BZ2_DECLINED;
     TICK(1);
     // ---- sorted rotations: suffix array of the least rotation (a Lyndon word) with a sentinel
-    const int r = least_rotation(block, nb);
-    S.rot.resize((size_t)nb + 1);
-    memcpy(S.rot.data(), block + r, (size_t)(nb - r));
-    memcpy(S.rot.data() + (nb - r), block, (size_t)r);
-    S.sa.resize((size_t)nb + 1);
+    if (S.rot.size() < (size_t)2 * nb + 8) S.rot.resize((size_t)2 * nb + 8);
+    memcpy(S.rot.data(), block, (size_t)nb);
+    memcpy(S.rot.data() + nb, block, (size_t)nb);
+    memset(S.rot.data() + 2 * (size_t)nb, 0, 8);
+    const int r = least_rotation(S.rot.data(), nb);
+    const unsigned char* rot = S.rot.data() + r;             // the least rotation, nb bytes
+    if (S.sa.size() < (size_t)nb + 1) S.sa.resize((size_t)nb + 1);
     int* SA = S.sa.data();
     TICK(2);
     if (nb == 1) {
@@ -337,8 +343,8 @@ extern "C" int rpcc_bz2_compress(const uint8_t* src, size_t n, uint8_t* dst, siz
     } else {
       // symbols shifted by one so that the sentinel 0 is unique and smallest: done on a 16-bit copy
       static thread_local std::vector<unsigned short> sym;
-      sym.resize((size_t)nb + 1);
-      for (int q = 0; q < nb; ++q) sym[q] = (unsigned short)(S.rot[q] + 1);
+      if (sym.size() < (size_t)nb + 1) sym.resize((size_t)nb + 1);
+      for (int q = 0; q < nb; ++q) sym[q] = (unsigned short)(rot[q] + 1);
       sym[nb] = 0;
       sais<unsigned short>(sym.data(), SA, nb + 1, 257);
     }
@@ -364,7 +370,7 @@ extern "C" int rpcc_bz2_compress(const uint8_t* src, size_t n, uint8_t* dst, siz
     const int EOB = nInUse + 1;
     int mtfFreq[kMaxAlpha];
     for (int q = 0; q <= EOB; ++q) mtfFreq[q] = 0;
-    S.mtfv.resize((size_t)nb + 2);
+    if (S.mtfv.size() < (size_t)nb + 2) S.mtfv.resize((size_t)nb + 2);
     unsigned short* mtfv = S.mtfv.data();
     alignas(16) unsigned char yy[256 + 16];                   // (padded: the search below reads 16 entries at a time)
     for (int q = 0; q < 256 + 16; ++q) yy[q] = (unsigned char)q;
